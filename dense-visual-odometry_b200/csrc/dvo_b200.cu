@@ -1,0 +1,494 @@
+// libdvo_b200.so — C ABI (include/dvo_b200.h) over the sm_100a kernels.
+// Build: nvcc -shared -Xcompiler -fPIC -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 (see __graft_entry__.build).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+
+#include "../../include/dvo_b200.h"
+#include "align_kernel.cuh"
+#include "pyramid_kernels.cuh"
+
+using namespace dvo;
+
+struct dvo_handle {
+    int device = 0, H = 0, W = 0, levels = 0, max_frames = 0, max_pairs = 0;
+    dvo_config cfg{};
+    bool intrinsics_set = false;
+    float fx = 0, fy = 0, cx = 0, cy = 0;
+    double depth_scale = 0;
+    int clamp_thr = 65536;
+    int lw[DVO_MAX_LEVELS]{}, lh[DVO_MAX_LEVELS]{}, lpitch[DVO_MAX_LEVELS]{};
+    size_t lplane[DVO_MAX_LEVELS]{};
+    uint8_t* gray[DVO_MAX_LEVELS]{};
+    uint16_t* depth[DVO_MAX_LEVELS]{};
+    float2* grad[DVO_MAX_LEVELS]{};
+    float k4[DVO_MAX_LEVELS][4]{}, kinv4[DVO_MAX_LEVELS][4]{};
+    int* queue = nullptr;
+    float* scratch = nullptr;
+    size_t scratch_stride = 0;
+    int sm_count = 0, threads = 256, blocks_per_sm = 2, grid_max = 0;
+    uint8_t* stage_bgr = nullptr;
+    uint16_t* stage_depth = nullptr;
+    float* qt_init = nullptr;
+    float* qt_last = nullptr;
+    float* qt_out = nullptr;
+    float* qt_one = nullptr;  // 7 + 12 floats for dvo_residuals_jacobian
+    dvo_pair_stats* stats = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+    long long launches = 0;
+    std::string err;
+};
+
+static const char* kNullHandle = "null handle";
+
+#define DVO_CUDA(h, call)                                                                             \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            return DVO_ERR_CUDA;                                                                      \
+        }                                                                                             \
+    } while (0)
+
+static int fail(dvo_handle* h, int code, const char* msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+extern "C" void dvo_default_config(dvo_config* cfg) {
+    if (!cfg) return;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->max_iterations = 100;
+    cfg->max_increased_steps = 0;
+    cfg->tolerance = 1e-6f;
+    cfg->sigma_prior = -1.0f;
+    cfg->weights = DVO_W_NONE;
+    cfg->oob_mode = DVO_OOB_INCLUSIVE;
+    cfg->tdist_dof = 5.0f;
+    cfg->tdist_init_sigma = 5.0f;
+    cfg->tdist_tolerance = 1e-3f;
+    cfg->tdist_max_iterations = 50;
+    cfg->huber_k = 1.345f * 5.0f;
+    cfg->max_distance = 5.0f;
+}
+
+extern "C" const char* dvo_last_error(const dvo_handle* h) { return h ? h->err.c_str() : kNullHandle; }
+
+// ---- kernel dispatch ---------------------------------------------------------------------------
+typedef void (*align_fn)(const AlignParams);
+
+template <int T, int B>
+static align_fn pick_align(int w, int oob) {
+#define DVO_PICK(WM, OM) \
+    if (w == WM && oob == OM) return (align_fn)align_kernel<WM, OM, T, B>;
+    DVO_PICK(DVO_W_NONE, DVO_OOB_INCLUSIVE)
+    DVO_PICK(DVO_W_NONE, DVO_OOB_STRICT)
+    DVO_PICK(DVO_W_TDIST_REF, DVO_OOB_INCLUSIVE)
+    DVO_PICK(DVO_W_TDIST_REF, DVO_OOB_STRICT)
+    DVO_PICK(DVO_W_HUBER, DVO_OOB_INCLUSIVE)
+    DVO_PICK(DVO_W_HUBER, DVO_OOB_STRICT)
+#undef DVO_PICK
+    return nullptr;
+}
+
+static align_fn get_align(const dvo_handle* h) {
+    if (h->threads == 512) return pick_align<512, 1>(h->cfg.weights, h->cfg.oob_mode);
+    if (h->threads == 128) return pick_align<128, 4>(h->cfg.weights, h->cfg.oob_mode);
+    return pick_align<256, 2>(h->cfg.weights, h->cfg.oob_mode);
+}
+
+typedef void (*dump_fn)(const AlignParams, int, int, int, const float*, float, float*, float*, uint8_t*, uint8_t*,
+                        double*);
+static dump_fn get_dump(const dvo_handle* h) {
+    const int w = (h->cfg.weights == DVO_W_HUBER) ? DVO_W_HUBER : DVO_W_NONE;  // dump is unweighted unless Huber
+    if (w == DVO_W_HUBER)
+        return h->cfg.oob_mode == DVO_OOB_STRICT ? (dump_fn)dump_kernel<DVO_W_HUBER, DVO_OOB_STRICT>
+                                                 : (dump_fn)dump_kernel<DVO_W_HUBER, DVO_OOB_INCLUSIVE>;
+    return h->cfg.oob_mode == DVO_OOB_STRICT ? (dump_fn)dump_kernel<DVO_W_NONE, DVO_OOB_STRICT>
+                                             : (dump_fn)dump_kernel<DVO_W_NONE, DVO_OOB_INCLUSIVE>;
+}
+
+__global__ void pose_matrix_kernel(const float* qt, float* T12) {
+    PoseQT p;
+    for (int i = 0; i < 4; ++i) p.q[i] = qt[i];
+    for (int i = 0; i < 3; ++i) p.t[i] = qt[4 + i];
+    pose_matrix(p, T12);
+}
+
+// ---- lifetime ----------------------------------------------------------------------------------
+extern "C" int dvo_destroy(dvo_handle* h) {
+    if (!h) return DVO_ERR_INVALID;
+    cudaSetDevice(h->device);
+    for (int l = 0; l < DVO_MAX_LEVELS; ++l) {
+        cudaFree(h->gray[l]);
+        cudaFree(h->depth[l]);
+        cudaFree(h->grad[l]);
+    }
+    cudaFree(h->queue);
+    cudaFree(h->scratch);
+    cudaFree(h->stage_bgr);
+    cudaFree(h->stage_depth);
+    cudaFree(h->qt_init);
+    cudaFree(h->qt_last);
+    cudaFree(h->qt_out);
+    cudaFree(h->qt_one);
+    cudaFree(h->stats);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    delete h;
+    return DVO_OK;
+}
+
+static int create_impl(dvo_handle* h) {
+    DVO_CUDA(h, cudaSetDevice(h->device));
+    cudaDeviceProp prop;
+    DVO_CUDA(h, cudaGetDeviceProperties(&prop, h->device));
+    h->sm_count = prop.multiProcessorCount;
+    int w = h->W, hh = h->H;
+    for (int l = 0; l < h->levels; ++l) {
+        h->lw[l] = w;
+        h->lh[l] = hh;
+        h->lpitch[l] = (w + 15) & ~15;
+        h->lplane[l] = (size_t)hh * h->lpitch[l];
+        const size_t n = h->lplane[l] * h->max_frames;
+        DVO_CUDA(h, cudaMalloc(&h->gray[l], n));
+        DVO_CUDA(h, cudaMalloc(&h->depth[l], n * sizeof(uint16_t)));
+        DVO_CUDA(h, cudaMalloc(&h->grad[l], n * sizeof(float2)));
+        DVO_CUDA(h, cudaMemset(h->gray[l], 0, n));
+        DVO_CUDA(h, cudaMemset(h->depth[l], 0, n * sizeof(uint16_t)));
+        DVO_CUDA(h, cudaMemset(h->grad[l], 0, n * sizeof(float2)));
+        w = (w + 1) / 2;   // image_pyramid.py:21 / :84-85 (ceil division)
+        hh = (hh + 1) / 2;
+    }
+    h->threads = h->cfg.threads_per_block ? h->cfg.threads_per_block : 256;
+    if (h->threads != 128 && h->threads != 256 && h->threads != 512) {
+        h->err = "threads_per_block must be 0, 128, 256 or 512";
+        return DVO_ERR_INVALID;
+    }
+    align_fn fn = get_align(h);
+    if (!fn) {
+        h->err = "unsupported weights / oob_mode";
+        return DVO_ERR_INVALID;
+    }
+    int occ = 0;
+    DVO_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, h->threads, 0));
+    if (occ < 1) occ = 1;
+    h->blocks_per_sm = h->cfg.blocks_per_sm > 0 ? (h->cfg.blocks_per_sm < occ ? h->cfg.blocks_per_sm : occ) : occ;
+    h->grid_max = h->sm_count * h->blocks_per_sm;
+    DVO_CUDA(h, cudaMalloc(&h->queue, sizeof(int)));
+    if (h->cfg.weights == DVO_W_TDIST_REF) {
+        h->scratch_stride = h->lplane[0];
+        DVO_CUDA(h, cudaMalloc(&h->scratch, h->scratch_stride * sizeof(float) * (size_t)h->grid_max));
+    }
+    DVO_CUDA(h, cudaMalloc(&h->qt_init, sizeof(float) * 7 * h->max_pairs));
+    DVO_CUDA(h, cudaMalloc(&h->qt_last, sizeof(float) * 7 * h->max_pairs));
+    DVO_CUDA(h, cudaMalloc(&h->qt_out, sizeof(float) * 7 * h->max_pairs));
+    DVO_CUDA(h, cudaMalloc(&h->qt_one, sizeof(float) * 32));
+    DVO_CUDA(h, cudaMalloc(&h->stats, sizeof(dvo_pair_stats) * h->max_pairs));
+    DVO_CUDA(h, cudaEventCreate(&h->ev0));
+    DVO_CUDA(h, cudaEventCreate(&h->ev1));
+    return DVO_OK;
+}
+
+extern "C" int dvo_create(dvo_handle** out, int device, int height, int width, int levels, int max_frames,
+                          int max_pairs, const dvo_config* cfg) {
+    if (!out) return DVO_ERR_INVALID;
+    *out = nullptr;
+    if (height < 1 || width < 1 || levels < 1 || levels > DVO_MAX_LEVELS || max_frames < 1 || max_pairs < 1)
+        return DVO_ERR_INVALID;
+    dvo_handle* h = new (std::nothrow) dvo_handle();
+    if (!h) return DVO_ERR_INVALID;
+    h->device = device;
+    h->H = height;
+    h->W = width;
+    h->levels = levels;
+    h->max_frames = max_frames;
+    h->max_pairs = max_pairs;
+    if (cfg)
+        h->cfg = *cfg;
+    else
+        dvo_default_config(&h->cfg);
+    *out = h;  // returned even on failure so the caller can read dvo_last_error, then dvo_destroy
+    return create_impl(h);
+}
+
+extern "C" int dvo_set_intrinsics(dvo_handle* h, float fx, float fy, float cx, float cy, double depth_scale) {
+    if (!h) return DVO_ERR_INVALID;
+    if (!(depth_scale >= 0.0)) return fail(h, DVO_ERR_INVALID, "depth_scale must be >= 0");
+    h->fx = fx; h->fy = fy; h->cx = cx; h->cy = cy;
+    h->depth_scale = depth_scale;
+    for (int l = 0; l < h->levels; ++l) {
+        // RGBDCameraModel.at (camera_model.py:62-79): K_l = S_l K in float32
+        const float s = ldexpf(1.0f, -l);
+        const float o = (l == 0) ? 0.0f : (ldexpf(1.0f, -l - 1) - 0.5f);
+        volatile float sx = s * cx, sy = s * cy;
+        const float fxl = s * fx, fyl = s * fy;
+        const float cxl = (l == 0) ? cx : (float)(sx + o), cyl = (l == 0) ? cy : (float)(sy + o);
+        h->k4[l][0] = fxl; h->k4[l][1] = fyl; h->k4[l][2] = cxl; h->k4[l][3] = cyl;
+        // np.linalg.inv(K_l) in float32 (camera_model.py:216): 1/fx and -(cx/fx), as LAPACK's gesv yields
+        volatile float ifx = 1.0f / fxl, ify = 1.0f / fyl;
+        volatile float qx = cxl / fxl, qy = cyl / fyl;
+        h->kinv4[l][0] = ifx; h->kinv4[l][1] = ify; h->kinv4[l][2] = -qx; h->kinv4[l][3] = -qy;
+    }
+    // base_dense_visual_odometry.py:59: (depth * scale) > max_distance in float64
+    h->clamp_thr = 65536;
+    for (int d = 0; d < 65536; ++d) {
+        volatile double m = (double)d * depth_scale;
+        if (m > (double)h->cfg.max_distance) {
+            h->clamp_thr = d;
+            break;
+        }
+    }
+    h->intrinsics_set = true;
+    return DVO_OK;
+}
+
+extern "C" int dvo_depth_clamp_threshold(const dvo_handle* h, int* threshold) {
+    if (!h || !threshold) return DVO_ERR_INVALID;
+    if (!h->intrinsics_set) return DVO_ERR_STATE;
+    *threshold = h->clamp_thr;
+    return DVO_OK;
+}
+
+extern "C" int dvo_level_shape(const dvo_handle* h, int level, int* height, int* width) {
+    if (!h || level < 0 || level >= h->levels) return DVO_ERR_RANGE;
+    if (height) *height = h->lh[level];
+    if (width) *width = h->lw[level];
+    return DVO_OK;
+}
+
+extern "C" int dvo_level_intrinsics(const dvo_handle* h, int level, float* k4) {
+    if (!h || !k4 || level < 0 || level >= h->levels) return DVO_ERR_RANGE;
+    if (!h->intrinsics_set) return DVO_ERR_STATE;
+    for (int i = 0; i < 4; ++i) k4[i] = h->k4[level][i];
+    return DVO_OK;
+}
+
+extern "C" long long dvo_launch_count(const dvo_handle* h) { return h ? h->launches : 0; }
+
+// ---- pyramids ----------------------------------------------------------------------------------
+static int build_levels(dvo_handle* h, int frame_base, int n_frames, int with_gradients, cudaStream_t st) {
+    for (int l = 1; l < h->levels; ++l) {
+        dim3 grid((h->lw[l] + 255) / 256, h->lh[l], n_frames);
+        median3_down_kernel<uint8_t><<<grid, 256, 0, st>>>(
+            h->gray[l - 1] + (size_t)frame_base * h->lplane[l - 1], h->gray[l] + (size_t)frame_base * h->lplane[l],
+            h->lw[l - 1], h->lh[l - 1], h->lpitch[l - 1], h->lplane[l - 1], h->lw[l], h->lh[l], h->lpitch[l],
+            h->lplane[l]);
+        median3_down_kernel<uint16_t><<<grid, 256, 0, st>>>(
+            h->depth[l - 1] + (size_t)frame_base * h->lplane[l - 1], h->depth[l] + (size_t)frame_base * h->lplane[l],
+            h->lw[l - 1], h->lh[l - 1], h->lpitch[l - 1], h->lplane[l - 1], h->lw[l], h->lh[l], h->lpitch[l],
+            h->lplane[l]);
+        h->launches += 2;
+    }
+    if (with_gradients) {
+        for (int l = 0; l < h->levels; ++l) {
+            dim3 grid((h->lw[l] + 255) / 256, h->lh[l], n_frames);
+            sobel3_kernel<<<grid, 256, 0, st>>>(h->gray[l] + (size_t)frame_base * h->lplane[l],
+                                                h->grad[l] + (size_t)frame_base * h->lplane[l], h->lw[l], h->lh[l],
+                                                h->lpitch[l], h->lplane[l]);
+            h->launches += 1;
+        }
+    }
+    DVO_CUDA(h, cudaGetLastError());
+    return DVO_OK;
+}
+
+static int build_impl(dvo_handle* h, int frame_base, const uint8_t* img, uint16_t* depth, int n_frames,
+                      int with_gradients, bool has_bgr, bool clamp, cudaStream_t st) {
+    if (!h) return DVO_ERR_INVALID;
+    if (!img || !depth) return fail(h, DVO_ERR_INVALID, "null image pointer");
+    if (n_frames < 1 || frame_base < 0 || frame_base + n_frames > h->max_frames)
+        return fail(h, DVO_ERR_RANGE, "frame slots out of range");
+    if (clamp && !h->intrinsics_set) return fail(h, DVO_ERR_STATE, "dvo_set_intrinsics must be called first");
+    DVO_CUDA(h, cudaSetDevice(h->device));
+    const int gpr = (h->W + 3) / 4;
+    dim3 grid((gpr * h->H + 255) / 256, n_frames);
+    const bool vec = (h->W % 4 == 0) && (((uintptr_t)img & 3) == 0) && (((uintptr_t)depth & 7) == 0);
+    uint8_t* g0 = h->gray[0] + (size_t)frame_base * h->lplane[0];
+    uint16_t* d0 = h->depth[0] + (size_t)frame_base * h->lplane[0];
+#define DVO_LAUNCH_GC(V, B)                                                                                        \
+    gray_clamp_kernel<V, B><<<grid, 256, 0, st>>>(img, depth, g0, d0, h->W, h->H, h->lpitch[0], h->lplane[0],    \
+                                                  h->clamp_thr, clamp ? 1 : 0)
+    if (vec && has_bgr) DVO_LAUNCH_GC(true, true);
+    else if (vec) DVO_LAUNCH_GC(true, false);
+    else if (has_bgr) DVO_LAUNCH_GC(false, true);
+    else DVO_LAUNCH_GC(false, false);
+#undef DVO_LAUNCH_GC
+    h->launches += 1;
+    return build_levels(h, frame_base, n_frames, with_gradients, st);
+}
+
+extern "C" int dvo_build_pyramids(dvo_handle* h, int frame_base, const uint8_t* bgr_dev, uint16_t* depth_dev,
+                                  int n_frames, int with_gradients, void* stream) {
+    return build_impl(h, frame_base, bgr_dev, depth_dev, n_frames, with_gradients, true, true, (cudaStream_t)stream);
+}
+
+extern "C" int dvo_build_pyramids_gray(dvo_handle* h, int frame_base, const uint8_t* gray_dev,
+                                       const uint16_t* depth_dev, int n_frames, int with_gradients, void* stream) {
+    return build_impl(h, frame_base, gray_dev, const_cast<uint16_t*>(depth_dev), n_frames, with_gradients, false,
+                      false, (cudaStream_t)stream);
+}
+
+extern "C" int dvo_build_pyramids_host(dvo_handle* h, int frame_base, const uint8_t* bgr_host,
+                                       const uint16_t* depth_host, int n_frames, int with_gradients, void* stream) {
+    if (!h) return DVO_ERR_INVALID;
+    if (!bgr_host || !depth_host) return fail(h, DVO_ERR_INVALID, "null image pointer");
+    if (n_frames < 1 || frame_base < 0 || frame_base + n_frames > h->max_frames)
+        return fail(h, DVO_ERR_RANGE, "frame slots out of range");
+    DVO_CUDA(h, cudaSetDevice(h->device));
+    const size_t px = (size_t)h->H * h->W;
+    if (!h->stage_bgr) {
+        DVO_CUDA(h, cudaMalloc(&h->stage_bgr, px * 3 * h->max_frames));
+        DVO_CUDA(h, cudaMalloc(&h->stage_depth, px * sizeof(uint16_t) * h->max_frames));
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* sb = h->stage_bgr + px * 3 * frame_base;
+    uint16_t* sd = h->stage_depth + px * frame_base;
+    DVO_CUDA(h, cudaMemcpyAsync(sb, bgr_host, px * 3 * n_frames, cudaMemcpyHostToDevice, st));
+    DVO_CUDA(h, cudaMemcpyAsync(sd, depth_host, px * sizeof(uint16_t) * n_frames, cudaMemcpyHostToDevice, st));
+    return build_impl(h, frame_base, sb, sd, n_frames, with_gradients, true, true, st);
+}
+
+extern "C" int dvo_get_pyramid(dvo_handle* h, int slot, int level, uint8_t* gray_dev, uint16_t* depth_dev,
+                               float* gx_dev, float* gy_dev, void* stream) {
+    if (!h) return DVO_ERR_INVALID;
+    if (slot < 0 || slot >= h->max_frames || level < 0 || level >= h->levels)
+        return fail(h, DVO_ERR_RANGE, "slot / level out of range");
+    DVO_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int w = h->lw[level], hh = h->lh[level], pitch = h->lpitch[level];
+    dim3 grid((w + 255) / 256, hh);
+    const size_t off = (size_t)slot * h->lplane[level];
+    if (gray_dev) unpitch_kernel<uint8_t><<<grid, 256, 0, st>>>(h->gray[level] + off, gray_dev, w, hh, pitch);
+    if (depth_dev) unpitch_kernel<uint16_t><<<grid, 256, 0, st>>>(h->depth[level] + off, depth_dev, w, hh, pitch);
+    if (gx_dev || gy_dev) unpitch_grad_kernel<<<grid, 256, 0, st>>>(h->grad[level] + off, gx_dev, gy_dev, w, hh, pitch);
+    h->launches += (gray_dev != nullptr) + (depth_dev != nullptr) + ((gx_dev || gy_dev) ? 1 : 0);
+    DVO_CUDA(h, cudaGetLastError());
+    return DVO_OK;
+}
+
+// ---- estimate ----------------------------------------------------------------------------------
+static void fill_params(const dvo_handle* h, AlignParams& p) {
+    memset(&p, 0, sizeof(p));
+    for (int l = 0; l < h->levels; ++l) {
+        LevelGeom& g = p.lv[l];
+        g.gray = h->gray[l];
+        g.depth = h->depth[l];
+        g.grad = h->grad[l];
+        g.plane = h->lplane[l];
+        g.w = h->lw[l];
+        g.h = h->lh[l];
+        g.pitch = h->lpitch[l];
+        g.n_groups = (int)(h->lplane[l] / 4);
+        g.fx = h->k4[l][0]; g.fy = h->k4[l][1]; g.cx = h->k4[l][2]; g.cy = h->k4[l][3];
+        g.ifx = h->kinv4[l][0]; g.ify = h->kinv4[l][1]; g.icx = h->kinv4[l][2]; g.icy = h->kinv4[l][3];
+    }
+    p.levels = h->levels;
+    p.max_iterations = h->cfg.max_iterations;
+    p.max_increased_steps = h->cfg.max_increased_steps;
+    p.tolerance = h->cfg.tolerance;
+    p.sigma_prior = h->cfg.sigma_prior;
+    p.tdist_dof = h->cfg.tdist_dof;
+    p.tdist_lambda0 = 1.0f / (h->cfg.tdist_init_sigma * h->cfg.tdist_init_sigma);
+    p.tdist_tol = h->cfg.tdist_tolerance;
+    p.tdist_max_iter = h->cfg.tdist_max_iterations;
+    p.huber_k = h->cfg.huber_k;
+    const float s_hi = (float)h->depth_scale;
+    p.scale_hi = s_hi;
+    p.scale_lo = (float)(h->depth_scale - (double)s_hi);
+    p.queue = h->queue;
+    p.scratch = h->scratch;
+    p.scratch_stride = h->scratch_stride;
+}
+
+extern "C" int dvo_estimate(dvo_handle* h, int prev_base, int cur_base, int n_pairs, const float* init_qt_dev,
+                            const float* last_qt_dev, float* out_qt_dev, dvo_pair_stats* stats_dev, void* stream) {
+    if (!h) return DVO_ERR_INVALID;
+    if (!out_qt_dev) return fail(h, DVO_ERR_INVALID, "out_qt is null");
+    if (!h->intrinsics_set) return fail(h, DVO_ERR_STATE, "dvo_set_intrinsics must be called first");
+    if (n_pairs < 1 || prev_base < 0 || cur_base < 0 || prev_base + n_pairs > h->max_frames ||
+        cur_base + n_pairs > h->max_frames)
+        return fail(h, DVO_ERR_RANGE, "pair range exceeds the frame slots");
+    DVO_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    AlignParams p;
+    fill_params(h, p);
+    p.n_pairs = n_pairs;
+    p.prev_base = prev_base;
+    p.cur_base = cur_base;
+    p.init_qt = init_qt_dev;
+    p.last_qt = last_qt_dev;
+    p.out_qt = out_qt_dev;
+    p.stats = stats_dev;
+    DVO_CUDA(h, cudaMemsetAsync(h->queue, 0, sizeof(int), st));
+    const int grid = n_pairs < h->grid_max ? n_pairs : h->grid_max;
+    align_fn fn = get_align(h);
+    DVO_CUDA(h, cudaEventRecord(h->ev0, st));
+    void* args[] = {&p};
+    DVO_CUDA(h, cudaLaunchKernel((const void*)fn, dim3(grid), dim3(h->threads), args, 0, st));
+    DVO_CUDA(h, cudaEventRecord(h->ev1, st));
+    h->ev_valid = true;
+    h->launches += 1;
+    return DVO_OK;
+}
+
+extern "C" int dvo_estimate_host(dvo_handle* h, int prev_base, int cur_base, int n_pairs, const float* init_qt_host,
+                                 const float* last_qt_host, float* out_qt_host, dvo_pair_stats* stats_host,
+                                 void* stream) {
+    if (!h) return DVO_ERR_INVALID;
+    if (!out_qt_host) return fail(h, DVO_ERR_INVALID, "out_qt is null");
+    if (n_pairs < 1 || n_pairs > h->max_pairs) return fail(h, DVO_ERR_RANGE, "n_pairs exceeds max_pairs");
+    DVO_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t qb = sizeof(float) * 7 * n_pairs;
+    if (init_qt_host) DVO_CUDA(h, cudaMemcpyAsync(h->qt_init, init_qt_host, qb, cudaMemcpyHostToDevice, st));
+    if (last_qt_host) DVO_CUDA(h, cudaMemcpyAsync(h->qt_last, last_qt_host, qb, cudaMemcpyHostToDevice, st));
+    const int rc = dvo_estimate(h, prev_base, cur_base, n_pairs, init_qt_host ? h->qt_init : nullptr,
+                                last_qt_host ? h->qt_last : nullptr, h->qt_out, h->stats, st);
+    if (rc != DVO_OK) return rc;
+    DVO_CUDA(h, cudaMemcpyAsync(out_qt_host, h->qt_out, qb, cudaMemcpyDeviceToHost, st));
+    if (stats_host)
+        DVO_CUDA(h, cudaMemcpyAsync(stats_host, h->stats, sizeof(dvo_pair_stats) * n_pairs, cudaMemcpyDeviceToHost, st));
+    return DVO_OK;
+}
+
+extern "C" int dvo_last_estimate_ms(dvo_handle* h, float* ms) {
+    if (!h || !ms) return DVO_ERR_INVALID;
+    if (!h->ev_valid) return fail(h, DVO_ERR_STATE, "no estimate has been launched");
+    DVO_CUDA(h, cudaSetDevice(h->device));
+    DVO_CUDA(h, cudaEventSynchronize(h->ev1));
+    DVO_CUDA(h, cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return DVO_OK;
+}
+
+extern "C" int dvo_residuals_jacobian(dvo_handle* h, int prev_slot, int cur_slot, int level, const float* qt_host,
+                                      float* r_dev, float* J_dev, uint8_t* depth_mask_dev, uint8_t* warp_valid_dev,
+                                      double* acc_dev, void* stream) {
+    if (!h) return DVO_ERR_INVALID;
+    if (!qt_host) return fail(h, DVO_ERR_INVALID, "qt is null");
+    if (!h->intrinsics_set) return fail(h, DVO_ERR_STATE, "dvo_set_intrinsics must be called first");
+    if (prev_slot < 0 || prev_slot >= h->max_frames || cur_slot < 0 || cur_slot >= h->max_frames || level < 0 ||
+        level >= h->levels)
+        return fail(h, DVO_ERR_RANGE, "slot / level out of range");
+    DVO_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    AlignParams p;
+    fill_params(h, p);
+    DVO_CUDA(h, cudaMemcpyAsync(h->qt_one, qt_host, sizeof(float) * 7, cudaMemcpyHostToDevice, st));
+    pose_matrix_kernel<<<1, 1, 0, st>>>(h->qt_one, h->qt_one + 16);
+    if (acc_dev) DVO_CUDA(h, cudaMemsetAsync(acc_dev, 0, sizeof(double) * DVO_ACC_TERMS, st));
+    dump_fn fn = get_dump(h);
+    const int n_groups = (int)(h->lplane[level] / 4);
+    const float* T12 = h->qt_one + 16;
+    float lambda = 0.0f;
+    void* args[] = {&p, &level, &prev_slot, &cur_slot, &T12, &lambda, &r_dev, &J_dev, &depth_mask_dev,
+                    &warp_valid_dev, &acc_dev};
+    DVO_CUDA(h, cudaLaunchKernel((const void*)fn, dim3((n_groups + 255) / 256), dim3(256), args, 0, st));
+    h->launches += 2;
+    return DVO_OK;
+}

@@ -1,0 +1,439 @@
+"""Host-side mirror of the reference's estimator interface over the C ABI (include/dvo_b200.h).
+
+`RobustDVOB200` keeps the reference's surface — constructor kwargs of `BaseRobustDVO`
+(core/robust_dense_visual_odometry/base_robust_dvo.py:34-83), `step()` / `current_pose`
+(core/base_dense_visual_odometry.py:54-91) and the four backend hooks
+(base_robust_dvo.py:91-135) — while all arithmetic of the path runs in libdvo_b200.so on the GPU.
+`PairBatchAligner` is the throughput form: B independent frame pairs per call.
+
+PyTorch is used for device/pinned memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _cabi
+from .lie import Se3, pose_to_qt
+
+logger = logging.getLogger(__name__)
+
+_WEIGHTS = {"none": _cabi.W_NONE, "tdist": _cabi.W_TDIST_REF, "huber": _cabi.W_HUBER}
+_OOB = {"inclusive": _cabi.OOB_INCLUSIVE, "strict": _cabi.OOB_STRICT}
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise _cabi.DvoError("a CUDA device is required: this path has no CPU fallback")
+    return torch
+
+
+def _stream_ptr(torch, device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _intrinsics_of(camera_model) -> Tuple[float, float, float, float, float]:
+    K = np.asarray(camera_model.intrinsics, dtype=np.float32)
+    return float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]), float(camera_model.depth_scale)
+
+
+class _Handle:
+    """Owns one dvo_handle."""
+
+    def __init__(self, device: int, height: int, width: int, levels: int, max_frames: int, max_pairs: int, cfg):
+        self.lib = _cabi.load()
+        self.ptr = C.c_void_p()
+        rc = self.lib.dvo_create(C.byref(self.ptr), device, height, width, levels, max_frames, max_pairs,
+                                 C.byref(cfg))
+        if rc != 0:
+            msg = self.lib.dvo_last_error(self.ptr)
+            if self.ptr:
+                self.lib.dvo_destroy(self.ptr)
+            raise _cabi.DvoError(f"dvo_create failed with status {rc}: {msg.decode() if msg else ''}")
+        self.height, self.width, self.levels = height, width, levels
+        self.max_frames, self.max_pairs = max_frames, max_pairs
+
+    def call(self, name, *args):
+        rc = getattr(self.lib, name)(self.ptr, *args)
+        _cabi.check(self.lib, self.ptr, rc, name)
+
+    def level_shape(self, level):
+        h, w = C.c_int(), C.c_int()
+        self.call("dvo_level_shape", level, C.byref(h), C.byref(w))
+        return h.value, w.value
+
+    def clamp_threshold(self) -> int:
+        t = C.c_int()
+        self.call("dvo_depth_clamp_threshold", C.byref(t))
+        return t.value
+
+    def launch_count(self) -> int:
+        return int(self.lib.dvo_launch_count(self.ptr))
+
+    def last_estimate_ms(self) -> float:
+        ms = C.c_float()
+        self.call("dvo_last_estimate_ms", C.byref(ms))
+        return ms.value
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.lib.dvo_destroy(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def make_config(use_weighter=False, max_increased_steps_allowed=0, sigma=None, tolerance=1e-6, max_iterations=100,
+                weights: Optional[str] = None, oob_mode="inclusive", huber_k=None, max_distance=5.0,
+                threads_per_block=0, blocks_per_sm=0):
+    lib = _cabi.load()
+    cfg = _cabi.dvo_config()
+    lib.dvo_default_config(C.byref(cfg))
+    if weights is None:
+        weights = "tdist" if use_weighter else "none"
+    if weights not in _WEIGHTS:
+        raise ValueError(f"weights must be one of {list(_WEIGHTS)}, got '{weights}'")
+    if oob_mode not in _OOB:
+        raise ValueError(f"oob_mode must be one of {list(_OOB)}, got '{oob_mode}'")
+    cfg.weights = _WEIGHTS[weights]
+    cfg.oob_mode = _OOB[oob_mode]
+    cfg.max_iterations = int(max_iterations)
+    cfg.max_increased_steps = int(max_increased_steps_allowed)
+    cfg.tolerance = float(tolerance)
+    cfg.sigma_prior = float(sigma) if sigma is not None else -1.0
+    if huber_k is not None:
+        cfg.huber_k = float(huber_k)
+    cfg.max_distance = float(max_distance)
+    cfg.threads_per_block = int(threads_per_block)
+    cfg.blocks_per_sm = int(blocks_per_sm)
+    return cfg
+
+
+def stats_to_numpy(buf: np.ndarray):
+    """uint8 [B,128] -> dict of arrays (dvo_pair_stats)."""
+    raw = np.ascontiguousarray(buf).view(np.int32).reshape(-1, 32)
+    L = _cabi.DVO_MAX_LEVELS
+    return dict(iters=raw[:, :L].copy(), n_valid=raw[:, L:2 * L].copy(),
+                err=raw[:, 2 * L:3 * L].copy().view(np.float32), flags=raw[:, 3 * L].copy())
+
+
+class RobustDVOB200:
+    """Drop-in for `RobustDVOCPU` / `RobustDVOGPU` on a B200.
+
+    Constructor arguments follow base_robust_dvo.py:34-83 (plus `height`/`width` as in
+    gpu_robust_dense_visual_odometry.py:17; if omitted the device state is created on the first frame).
+    Extras, all defaulting to reference behaviour: `weights` ("none" | "tdist" | "huber"), `oob_mode`
+    ("inclusive" | "strict"), `huber_k`, `max_distance`, `device`.
+    """
+
+    def __init__(self, camera_model, initial_pose, levels: int, use_weighter: bool = False,
+                 max_increased_steps_allowed: int = 0, sigma: float = None, tolerance: float = 1e-6,
+                 max_iterations: int = 100, approximate_image2_gradient: bool = False, height: int = None,
+                 width: int = None, weights: Optional[str] = None, oob_mode: str = "inclusive",
+                 huber_k: float = None, max_distance: float = 5.0, device: int = 0):
+        if approximate_image2_gradient:
+            raise NotImplementedError("approximate_image2_gradient=True is not built yet (SURVEY §8f item 4)")
+        if levels < 1 or levels > _cabi.DVO_MAX_LEVELS:
+            raise ValueError(f"levels must be in [1, {_cabi.DVO_MAX_LEVELS}], got {levels}")
+        self._camera_model = camera_model
+        self._initial_pose = initial_pose
+        self._current_pose = self._as_local(initial_pose)
+        self._last_pose = None
+        self._last_estimated_transform = None
+        self._levels = int(levels)
+        self._sigma = sigma
+        self._max_distance = max_distance
+        self._device = device
+        self._cfg = make_config(use_weighter, max_increased_steps_allowed, sigma, tolerance, max_iterations, weights,
+                                oob_mode, huber_k, max_distance)
+        self._h: Optional[_Handle] = None
+        self._have_prev = False
+        self._prev_slot = 0           # step(): slot holding the previous frame
+        self._hook_slots = (2, 3)     # _build_pyramids hook: (prev, cur)
+        self._host_prev = None        # lazily fetched (gray, depth) of the previous frame
+        self.last_stats = None
+        if height is not None and width is not None:
+            self._ensure(int(height), int(width))
+
+    # ------------------------------------------------------------------ plumbing
+    @staticmethod
+    def _as_local(pose) -> Se3:
+        return Se3.from_qt(pose_to_qt(pose))
+
+    def _ensure(self, height: int, width: int):
+        if self._h is not None:
+            if (self._h.height, self._h.width) != (height, width):
+                raise ValueError(f"frame size changed from {(self._h.height, self._h.width)} to {(height, width)}")
+            return
+        torch = _torch()
+        self._torch = torch
+        self._h = _Handle(self._device, height, width, self._levels, 4, 1, self._cfg)
+        fx, fy, cx, cy, scale = _intrinsics_of(self._camera_model)
+        self._h.call("dvo_set_intrinsics", fx, fy, cx, cy, scale)
+        self._clamp_thr = self._h.clamp_threshold()
+        dev = torch.device("cuda", self._device)
+        self._dev = dev
+        self._pin_bgr = torch.empty((height, width, 3), dtype=torch.uint8).pin_memory()
+        self._pin_depth = torch.empty((height, width), dtype=torch.uint16).pin_memory()
+        self._pin_qt = torch.empty((3, 7), dtype=torch.float32).pin_memory()   # init, last, out
+        self._pin_stats = torch.empty((_cabi.STATS_BYTES,), dtype=torch.uint8).pin_memory()
+
+    @property
+    def levels(self) -> int:
+        return self._levels
+
+    @property
+    def current_pose(self):
+        return self._current_pose
+
+    # ------------------------------------------------------------------ reference API
+    def step(self, color_image: np.ndarray, depth_image: np.ndarray, init_guess=None, **kwargs):
+        """base_dense_visual_odometry.py:54-87.  Returns the Se3 taking the previous camera frame to the
+        current one (identity for the first frame), or None if the estimate is not finite."""
+        if color_image.ndim != 3 or color_image.shape[2] != 3 or color_image.dtype != np.uint8:
+            raise ValueError("color_image must be HxWx3 uint8 (BGR)")
+        if depth_image.shape != color_image.shape[:2]:
+            raise ValueError("depth_image must be HxW")
+        h, w = depth_image.shape
+        self._ensure(h, w)
+        torch = self._torch
+        if depth_image.dtype != np.uint16:
+            # the reference accepts any integer dtype here (its own unit test passes uint8)
+            depth16 = depth_image.astype(np.uint16)
+        else:
+            depth16 = depth_image
+        st = _stream_ptr(torch, self._dev)
+        cur_slot = 1 - self._prev_slot
+        self._pin_bgr.numpy()[...] = color_image
+        self._pin_depth.numpy()[...] = depth16
+        self._h.call("dvo_build_pyramids_host", cur_slot, C.c_void_p(self._pin_bgr.data_ptr()),
+                     C.c_void_p(self._pin_depth.data_ptr()), 1, 1, st)
+        # the reference zeroes far depth in the caller's array (base_dense_visual_odometry.py:59)
+        if self._clamp_thr < 65536:
+            depth_image[depth_image >= self._clamp_thr] = 0
+
+        if not self._have_prev:
+            transform = Se3.identity()
+        else:
+            qt = self._pin_qt.numpy()
+            init_ptr = None
+            if init_guess is not None:
+                qt[0] = pose_to_qt(init_guess)
+                init_ptr = C.c_void_p(self._pin_qt[0].data_ptr())
+            last_ptr = None
+            if self._sigma is not None and self._last_estimated_transform is not None:
+                qt[1] = pose_to_qt(self._last_estimated_transform)
+                last_ptr = C.c_void_p(self._pin_qt[1].data_ptr())
+            self._h.call("dvo_estimate_host", self._prev_slot, cur_slot, 1, init_ptr, last_ptr,
+                         C.c_void_p(self._pin_qt[2].data_ptr()), C.c_void_p(self._pin_stats.data_ptr()), st)
+            torch.cuda.current_stream(self._dev).synchronize()
+            out = qt[2].copy()
+            self.last_stats = stats_to_numpy(self._pin_stats.numpy()[None, :])
+            transform = Se3.from_qt(out) if np.all(np.isfinite(out)) else None
+
+        if transform is not None:
+            self._last_pose = self._current_pose.copy()
+            self._last_estimated_transform = transform.copy()
+            self._current_pose = self._current_pose * transform.inverse()
+            self._prev_slot = cur_slot
+            self._have_prev = True
+            self._host_prev = None
+        else:
+            logger.warning("DVO could not estimate transform, trying luck on next frame..")
+        return transform
+
+    # ------------------------------------------------------------------ backend hooks
+    def _fetch_prev(self):
+        """Host copies of the previous frame's gray / clamped depth (level 0 of its slot)."""
+        if self._host_prev is None:
+            if not self._have_prev:
+                return None, None
+            self._host_prev = self.get_pyramid_level(self._prev_slot, 0)[:2]
+        return self._host_prev
+
+    @property
+    def _gray_image_prev(self):
+        return self._fetch_prev()[0]
+
+    @property
+    def _depth_image_prev(self):
+        return self._fetch_prev()[1]
+
+    def _build_pyramids(self, gray_image: np.ndarray, depth_image: np.ndarray):
+        """base_robust_dvo.py:119-125 / cpu_...py:44-52: previous-frame pyramids from the stored previous
+        frame, current-frame pyramids (and Sobel planes) from the arguments."""
+        if not self._have_prev:
+            raise NotImplementedError("no previous frame: call step() with a first frame before _build_pyramids")
+        torch = self._torch
+        st = _stream_ptr(torch, self._dev)
+        g = torch.as_tensor(np.ascontiguousarray(gray_image, dtype=np.uint8)).to(self._dev)
+        d = torch.as_tensor(np.ascontiguousarray(depth_image).astype(np.uint16)).to(self._dev)
+        ps, cs = self._hook_slots
+        pg, pd = self._fetch_prev()
+        pgt = torch.as_tensor(pg).to(self._dev)
+        pdt = torch.as_tensor(pd).to(self._dev)
+        self._h.call("dvo_build_pyramids_gray", ps, C.c_void_p(pgt.data_ptr()), C.c_void_p(pdt.data_ptr()), 1, 0, st)
+        self._h.call("dvo_build_pyramids_gray", cs, C.c_void_p(g.data_ptr()), C.c_void_p(d.data_ptr()), 1, 1, st)
+        torch.cuda.current_stream(self._dev).synchronize()
+        self._hook_ready = True
+
+    def _setup(self, level: int):
+        """Sobel planes of every level were built with the pyramid; nothing to do per level."""
+        if not 0 <= level < self._levels:
+            raise IndexError(f"'level' out of range [0, {self._levels - 1}], got {level} instead")
+
+    def _cleanup(self):
+        pass
+
+    def compute_residuals_and_jacobian(self, estimate, level: int = 0):
+        """base_robust_dvo.py:91-117: (residuals Nx1 f32, jacobian Nx6 f32, depth mask HxW bool) in masked
+        row-major pixel order, from the pyramids of the last `_build_pyramids` call."""
+        if not getattr(self, "_hook_ready", False):
+            raise NotImplementedError("Call to _build_pyramids did not correctly set pyramids")
+        r, J, mask, valid, _ = self.residuals_dense(estimate, level, self._hook_slots[0], self._hook_slots[1])
+        v = valid.reshape(-1)
+        return r.reshape(-1, 1)[v], J.reshape(-1, 6)[v], mask
+
+    def residuals_dense(self, estimate, level: int, prev_slot: int, cur_slot: int):
+        """Dense dump of one level: r [H,W], J [H,W,6], depth mask, warp-valid mask, acc[29] (float64)."""
+        torch = self._torch
+        hl, wl = self._h.level_shape(level)
+        st = _stream_ptr(torch, self._dev)
+        r = torch.empty((hl, wl), dtype=torch.float32, device=self._dev)
+        J = torch.empty((hl, wl, 6), dtype=torch.float32, device=self._dev)
+        m = torch.empty((hl, wl), dtype=torch.uint8, device=self._dev)
+        v = torch.empty((hl, wl), dtype=torch.uint8, device=self._dev)
+        acc = torch.empty((_cabi.DVO_ACC_TERMS,), dtype=torch.float64, device=self._dev)
+        qt = np.ascontiguousarray(pose_to_qt(estimate))
+        self._h.call("dvo_residuals_jacobian", prev_slot, cur_slot, level, qt.ctypes.data_as(C.c_void_p),
+                     C.c_void_p(r.data_ptr()), C.c_void_p(J.data_ptr()), C.c_void_p(m.data_ptr()),
+                     C.c_void_p(v.data_ptr()), C.c_void_p(acc.data_ptr()), st)
+        torch.cuda.current_stream(self._dev).synchronize()
+        return (r.cpu().numpy(), J.cpu().numpy(), m.cpu().numpy().astype(bool), v.cpu().numpy().astype(bool),
+                acc.cpu().numpy())
+
+    def get_pyramid_level(self, slot: int, level: int):
+        """(gray u8, depth u16, gx f32, gy f32) of one level of a frame slot, as host arrays."""
+        torch = self._torch
+        hl, wl = self._h.level_shape(level)
+        st = _stream_ptr(torch, self._dev)
+        g = torch.empty((hl, wl), dtype=torch.uint8, device=self._dev)
+        d = torch.empty((hl, wl), dtype=torch.uint16, device=self._dev)
+        gx = torch.empty((hl, wl), dtype=torch.float32, device=self._dev)
+        gy = torch.empty((hl, wl), dtype=torch.float32, device=self._dev)
+        self._h.call("dvo_get_pyramid", slot, level, C.c_void_p(g.data_ptr()), C.c_void_p(d.data_ptr()),
+                     C.c_void_p(gx.data_ptr()), C.c_void_p(gy.data_ptr()), st)
+        torch.cuda.current_stream(self._dev).synchronize()
+        return g.cpu().numpy(), d.cpu().numpy(), gx.cpu().numpy(), gy.cpu().numpy()
+
+
+class PairBatchAligner:
+    """B independent frame pairs per call (BASELINE.json configs 2-4): one persistent kernel launch runs
+    every pair's coarse-to-fine Gauss-Newton on the device.
+
+    Inputs may be CUDA tensors (resident path) or host arrays / pinned tensors (end-to-end path: the
+    copies are part of the call).  Frame slots: previous frames 0..B-1, current frames B..2B-1.
+    """
+
+    def __init__(self, camera_model, height: int, width: int, levels: int, max_pairs: int, device: int = 0,
+                 **cfg_kwargs):
+        torch = _torch()
+        self._torch = torch
+        self._dev = torch.device("cuda", device)
+        self.max_pairs = int(max_pairs)
+        self.levels = int(levels)
+        self._cfg = make_config(**cfg_kwargs)
+        self._h = _Handle(device, height, width, levels, 2 * self.max_pairs, self.max_pairs, self._cfg)
+        fx, fy, cx, cy, scale = _intrinsics_of(camera_model)
+        self._h.call("dvo_set_intrinsics", fx, fy, cx, cy, scale)
+        self.clamp_threshold = self._h.clamp_threshold()
+        self._qt = torch.empty((self.max_pairs, 7), dtype=torch.float32, device=self._dev)
+        self._stats = torch.empty((self.max_pairs, _cabi.STATS_BYTES), dtype=torch.uint8, device=self._dev)
+        self._pin_qt = torch.empty((self.max_pairs, 7), dtype=torch.float32).pin_memory()
+        self._pin_stats = torch.empty((self.max_pairs, _cabi.STATS_BYTES), dtype=torch.uint8).pin_memory()
+
+    @property
+    def handle(self) -> _Handle:
+        return self._h
+
+    def _ptr(self, t):
+        return C.c_void_p(t.data_ptr())
+
+    def build(self, bgr_prev, depth_prev, bgr_cur, depth_cur):
+        """Gray conversion, depth clamp (in place on device inputs), pyramids and gradient planes."""
+        torch = self._torch
+        B = bgr_prev.shape[0]
+        if B > self.max_pairs:
+            raise ValueError(f"batch {B} exceeds max_pairs {self.max_pairs}")
+        st = _stream_ptr(torch, self._dev)
+        if isinstance(bgr_prev, np.ndarray) or not bgr_prev.is_cuda:
+            as_t = (lambda a: torch.as_tensor(a)) if isinstance(bgr_prev, np.ndarray) else (lambda a: a)
+            bp, dp, bc, dc = (as_t(a).contiguous() for a in (bgr_prev, depth_prev, bgr_cur, depth_cur))
+            self._keep = (bp, dp, bc, dc)
+            self._h.call("dvo_build_pyramids_host", 0, self._ptr(bp), self._ptr(dp), B, 0, st)
+            self._h.call("dvo_build_pyramids_host", self.max_pairs, self._ptr(bc), self._ptr(dc), B, 1, st)
+        else:
+            self._h.call("dvo_build_pyramids", 0, self._ptr(bgr_prev), self._ptr(depth_prev), B, 0, st)
+            self._h.call("dvo_build_pyramids", self.max_pairs, self._ptr(bgr_cur), self._ptr(depth_cur), B, 1, st)
+        self._B = B
+
+    def estimate(self, init_qt=None, to_host: bool = True):
+        """Runs the GN kernel on the pairs of the last build().  Returns (qt [B,7], stats dict) as host arrays
+        when to_host, else the device tensors (no synchronisation)."""
+        torch = self._torch
+        B = self._B
+        st = _stream_ptr(torch, self._dev)
+        init_ptr = None
+        if init_qt is not None:
+            self._init = torch.as_tensor(np.asarray(init_qt, dtype=np.float32)).to(self._dev).contiguous()
+            init_ptr = self._ptr(self._init)
+        self._h.call("dvo_estimate", 0, self.max_pairs, B, init_ptr, None, self._ptr(self._qt), self._ptr(self._stats),
+                     st)
+        if not to_host:
+            return self._qt[:B], self._stats[:B]
+        self._pin_qt[:B].copy_(self._qt[:B], non_blocking=True)
+        self._pin_stats[:B].copy_(self._stats[:B], non_blocking=True)
+        torch.cuda.current_stream(self._dev).synchronize()
+        return self._pin_qt[:B].numpy().copy(), stats_to_numpy(self._pin_stats[:B].numpy())
+
+    def align(self, bgr_prev, depth_prev, bgr_cur, depth_cur, init_qt=None):
+        self.build(bgr_prev, depth_prev, bgr_cur, depth_cur)
+        return self.estimate(init_qt)
+
+    def last_kernel_ms(self) -> float:
+        return self._h.last_estimate_ms()
+
+    def launch_count(self) -> int:
+        return self._h.launch_count()
+
+
+def robust_dvo_factory(use_gpu: bool = True, **kwargs):
+    """Mirror of core/robust_dense_visual_odometry/__init__.py:5-25 with the B200 backend as the GPU branch.
+    There is no CPU branch here: `use_gpu=False` is an error, not a fallback."""
+    if not use_gpu:
+        raise ValueError("dense_visual_odometry_b200 has no CPU backend; use the reference for use_gpu=False")
+    return RobustDVOB200(**kwargs)
+
+
+_SUPPORTED_METHODS = {"robust-dvo": robust_dvo_factory}
+
+
+def get_dvo(method: str, camera_model, init_pose, **kwargs):
+    """Mirror of core/__init__.py:14-40 (same registry name, same error wrapping)."""
+    if method not in _SUPPORTED_METHODS:
+        raise ValueError("Not supported method '{}', available options are '{}'".format(
+            method, list(_SUPPORTED_METHODS.keys())))
+    try:
+        return _SUPPORTED_METHODS[method](camera_model=camera_model, initial_pose=init_pose, **kwargs)
+    except Exception as e:
+        raise ValueError((
+            "Could not dynamically load method '{}' with parameters '{}'".format(method, kwargs),
+            ", got the following exception: {}".format(e)))

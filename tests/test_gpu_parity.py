@@ -1,0 +1,362 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  The CUDA path, called through the C ABI by the
+host mirror, is compared with (a) the CPU oracle on the same inputs and (b) golden vectors produced by the
+REAL reference (tests/golden/).  Tolerances follow BASELINE.json's north_star:
+  pyramid indexing and validity masks: bit-exact; residuals / Jacobians: 1e-5 relative (to the plane's
+  max magnitude); final pose: 1e-4 rad / 1e-4 m."""
+import hashlib
+import json
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import dvo_oracle as O  # noqa: E402
+
+
+def _Km(K):
+    return np.array([[K[0], 0, K[2]], [0, K[1], K[3]], [0, 0, 1]], dtype=np.float32)
+
+
+def _dg(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def dvo_mod():
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    import dense_visual_odometry_b200 as m
+    return m
+
+
+def _estimator(m, K, scale, levels, **kw):
+    cam = m.RGBDCameraModel(_Km(K), scale)
+    return m.get_dvo("robust-dvo", cam, m.Se3.identity(), levels=levels, **kw)
+
+
+# ------------------------------------------------------------------------------------------------ a1, a2, a9
+def test_pyramids_bit_exact_vs_oracle_and_reference(dvo_mod, testdata_frames, golden_dir):
+    f = testdata_frames
+    prim = json.loads((golden_dir / "primitives.json").read_text())
+    est = _estimator(dvo_mod, f["K"], f["depth_scale"], 4)
+    for i in (0, 3):
+        d = f["depth"][i].copy()
+        est.step(f["bgr"][i], d)
+        assert int((d != f["depth"][i]).sum()) == prim[f"f{i}_clamped"]      # in-place clamp of the caller's array
+        gp = O.build_pyramid(O.bgr_to_gray(f["bgr"][i]), 4)
+        dp = O.build_pyramid(O.clamp_depth(f["depth"][i], f["depth_scale"]), 4)
+        for lv in range(4):
+            g, dd, gx, gy = est.get_pyramid_level(est._prev_slot, lv)
+            ogx, ogy = O.sobel3(gp[lv])
+            assert np.array_equal(g, gp[lv]) and np.array_equal(dd, dp[lv])
+            assert np.array_equal(gx, ogx) and np.array_equal(gy, ogy)
+            assert _dg(g) == prim[f"f{i}_gray_L{lv}"] and _dg(dd) == prim[f"f{i}_depth_L{lv}"]
+            assert _dg(gx) == prim[f"f{i}_gx_L{lv}"] and _dg(gy) == prim[f"f{i}_gy_L{lv}"]
+
+
+def test_pyramids_odd_size(dvo_mod, golden_dir):
+    prim = json.loads((golden_dir / "primitives.json").read_text())
+    rng = np.random.default_rng(7)
+    odd8 = rng.integers(0, 256, (77, 101), dtype=np.uint8)
+    odd16 = rng.integers(0, 65536, (77, 101), dtype=np.uint16)
+    odd16[rng.random((77, 101)) < 0.3] = 0
+    est = _estimator(dvo_mod, (100.0, 100.0, 50.0, 38.0), 1e-9, 4)   # scale so small that nothing is clamped
+    est.step(np.repeat(odd8[..., None], 3, -1), odd16.copy())
+    est._build_pyramids(odd8, odd16)
+    for lv in range(4):
+        g, d, gx, gy = est.get_pyramid_level(est._hook_slots[1], lv)
+        assert list(g.shape) == prim[f"odd_shape_L{lv}"]
+        assert _dg(g) == prim[f"odd_gray_L{lv}"] and _dg(d) == prim[f"odd_depth_L{lv}"]
+        assert _dg(gx) == prim[f"odd_gx_L{lv}"] and _dg(gy) == prim[f"odd_gy_L{lv}"]
+
+
+def test_gray_conversion_lattice(dvo_mod, golden_dir):
+    prim = json.loads((golden_dir / "primitives.json").read_text())
+    rng = np.random.default_rng(7)
+    rng.integers(0, 256, (77, 101), dtype=np.uint8)
+    rng.integers(0, 65536, (77, 101), dtype=np.uint16)
+    rng.random((77, 101))
+    lat = rng.integers(0, 256, (64, 64, 3), dtype=np.uint8)
+    est = _estimator(dvo_mod, (100.0, 100.0, 32.0, 32.0), 1e-9, 1)
+    est.step(lat, np.ones((64, 64), dtype=np.uint16))
+    g = est.get_pyramid_level(est._prev_slot, 0)[0]
+    assert _dg(g) == prim["lattice_gray"]
+
+
+# ------------------------------------------------------------------------------------------------ a3-a11, a13
+def _dense_oracle(ld, T, oob):
+    r, J, mask, valid = O.residuals_and_jacobian(ld, T, oob)
+    h, w = mask.shape
+    wv = np.zeros(h * w, dtype=bool)
+    idx = np.flatnonzero(mask.reshape(-1))
+    wv[idx[valid]] = True
+    rd = np.full(h * w, np.nan, dtype=np.float32)
+    Jd = np.zeros((h * w, 6), dtype=np.float32)
+    rd[wv] = r
+    Jd[wv] = J
+    return r, J, rd.reshape(h, w), Jd.reshape(h, w, 6), mask, wv.reshape(h, w)
+
+
+def _compare_level(est, m, ld, pose, lv, oob, report):
+    T = pose.exp()
+    r, J, rd, Jd, mask, wv = _dense_oracle(ld, T, oob)
+    gr, gJ, gmask, gvalid, acc = est.residuals_dense(pose, lv, est._hook_slots[0], est._hook_slots[1])
+    assert np.array_equal(gmask, mask), "depth mask must be bit-exact"
+    n_mis = int((gvalid != wv).sum())
+    report[f"L{lv}_valid_mismatch"] = n_mis
+    assert n_mis == 0, f"warp-valid mask differs at {n_mis} pixels"
+    both = wv
+    dr = np.abs(gr[both] - rd[both])
+    rs = max(float(np.abs(rd[both]).max()), 1.0)
+    dJ = np.abs(gJ[both] - Jd[both])
+    Js = float(np.abs(Jd[both]).max())
+    report[f"L{lv}_r_rel"] = float(dr.max() / rs)
+    report[f"L{lv}_J_rel"] = float(dJ.max() / Js)
+    assert dr.max() <= 1e-5 * rs, f"residuals differ by {dr.max()} (scale {rs})"
+    assert dJ.max() <= 1e-5 * Js, f"Jacobians differ by {dJ.max()} (scale {Js})"
+    # fused reduction of the same pass against float64 sums of the oracle's r, J
+    J64, r64 = J.astype(np.float64), r.astype(np.float64)
+    H = J64.T @ J64
+    g = J64.T @ r64
+    iu = np.triu_indices(6)
+    np.testing.assert_allclose(acc[:21], H[iu], rtol=2e-5, atol=2e-5 * np.abs(H).max())
+    np.testing.assert_allclose(acc[21:27], g, rtol=2e-5, atol=2e-5 * np.abs(g).max())
+    np.testing.assert_allclose(acc[27], (r64 ** 2).sum(), rtol=2e-5)
+    assert acc[28] == r.shape[0]
+
+
+@pytest.mark.parametrize("oob", ["inclusive", "strict"])
+def test_residuals_jacobian_dense_vs_oracle(dvo_mod, testdata_frames, oob):
+    m = dvo_mod
+    f = testdata_frames
+    Km = _Km(f["K"])
+    est = _estimator(m, f["K"], f["depth_scale"], 4, oob_mode=oob)
+    est.step(f["bgr"][0], f["depth"][0].copy())
+    d1 = O.clamp_depth(f["depth"][1], f["depth_scale"])
+    est._build_pyramids(O.bgr_to_gray(f["bgr"][1]), d1)
+    gp0 = O.build_pyramid(O.bgr_to_gray(f["bgr"][0]), 4)
+    dp0 = O.build_pyramid(O.clamp_depth(f["depth"][0], f["depth_scale"]), 4)
+    gp1 = O.build_pyramid(O.bgr_to_gray(f["bgr"][1]), 4)
+    poses = [m.Se3.identity(),
+             m.Se3.from_se3(np.array([[0.0017], [-0.0072], [-0.0108], [0.005], [0.0065], [0.0034]], np.float32)),
+             m.Se3.from_se3(np.array([[0.05], [-0.03], [0.08], [-0.04], [0.03], [0.06]], np.float32))]
+    report = {}
+    for lv in range(4):
+        ld = O.prepare_level(Km, f["depth_scale"], gp0[lv], dp0[lv], gp1[lv], lv)
+        for pose in poses:
+            _compare_level(est, m, ld, pose, lv, O.OOB_STRICT if oob == "strict" else O.OOB_INCLUSIVE, report)
+    print("dense parity:", report)
+
+
+@pytest.mark.parametrize("pair,variant", [(1, ""), (4, ""), (1, "_strict")])
+def test_first_iteration_vs_reference_golden(dvo_mod, testdata_frames, golden_dir, pair, variant):
+    """r, J (strided sample), H, b, err and counts of the REAL reference at the first iteration of each level."""
+    m = dvo_mod
+    f = testdata_frames
+    g = np.load(golden_dir / f"pose_testdata_{pair}_{pair + 1}{variant}.npz")
+    est = _estimator(m, f["K"], f["depth_scale"], 4, oob_mode="strict" if variant else "inclusive")
+    est.step(f["bgr"][pair - 1], f["depth"][pair - 1].copy())
+    est._build_pyramids(O.bgr_to_gray(f["bgr"][pair]), O.clamp_depth(f["depth"][pair], f["depth_scale"]))
+    for lv in range(4):
+        T = g[f"L{lv}_T"]
+        # rebuild the reference's estimate as a pose: golden stores Se3.exp(); recover q,t through So3
+        R = T[:3, :3].astype(np.float64)
+        pose = m.Se3(m.So3(R) if not np.allclose(R, np.eye(3), atol=0) else m.So3.identity(),
+                     T[:3, 3].reshape(3, 1).astype(np.float32))
+        est._setup(lv)
+        r, J, mask = est.compute_residuals_and_jacobian(pose, lv)
+        assert _dg(mask.astype(np.uint8)) == str(g[f"L{lv}_mask_digest"])
+        assert int(mask.sum()) == int(g[f"L{lv}_n_depth"])
+        if lv == 3 or np.allclose(R, np.eye(3), atol=0):
+            # the level started from exactly the pose the reference used: shapes must agree exactly
+            assert r.shape[0] == int(g[f"L{lv}_n"])
+            idx = g[f"L{lv}_idx"]
+            np.testing.assert_allclose(r[idx, 0], g[f"L{lv}_r"], atol=1e-5 * 255)
+            Jg = g[f"L{lv}_J"]
+            np.testing.assert_allclose(J[idx], Jg, atol=1e-5 * np.abs(Jg).max())
+            H = J.astype(np.float64).T @ J.astype(np.float64)
+            np.testing.assert_allclose(H, g[f"L{lv}_H"], rtol=1e-4)
+            np.testing.assert_allclose(np.mean(r.astype(np.float64) ** 2), g[f"L{lv}_err"], rtol=1e-5)
+        else:
+            assert abs(r.shape[0] - int(g[f"L{lv}_n"])) <= 0.002 * int(g[f"L{lv}_n"])
+
+
+def test_reference_unit_test_10x10(dvo_mod, golden_dir):
+    """The reference's own test (test_cpu_robust_dense_visual_odometry.py:20-44) against this backend."""
+    m = dvo_mod
+    g = np.full((10, 10), 150, dtype=np.uint8)
+    g[:5, :5] = 50
+    c = np.repeat(g[..., None], 3, axis=-1)
+    d = np.ones((10, 10), dtype=np.uint8)
+    d[:5, :5] = 3
+    cam = m.RGBDCameraModel(np.eye(3, dtype=np.float32), 1.0)
+    est = m.get_dvo("robust-dvo", cam, m.Se3.identity(), levels=1)
+    est.step(color_image=c, depth_image=d)
+    est._build_pyramids(gray_image=g, depth_image=d)
+    est._setup(level=0)
+    r, J, mask = est.compute_residuals_and_jacobian(estimate=m.Se3.identity(), level=0)
+    np.testing.assert_almost_equal(r, np.zeros((100, 1), dtype=np.float32))
+    ref = np.load(golden_dir / "unit10x10.npz")
+    np.testing.assert_allclose(J, ref["J"], rtol=1e-5, atol=1e-5 * np.abs(ref["J"]).max())
+    assert mask.shape == (10, 10) and mask.all()
+
+
+# ------------------------------------------------------------------------------------------------ a12-a17
+POSE_TOL = 1e-4
+
+
+def _check_pose(T, g, prefix=""):
+    q, t = T.so3.quat.reshape(4), T.tvec.reshape(3)
+    assert np.abs(q - g[prefix + "q"]).max() < POSE_TOL, (q, g[prefix + "q"])
+    assert np.abs(t - g[prefix + "t"]).max() < POSE_TOL, (t, g[prefix + "t"])
+    xi = T.log().reshape(6)
+    assert np.abs(xi - g[prefix + "xi"]).max() < POSE_TOL
+    return float(np.abs(xi - g[prefix + "xi"]).max())
+
+
+def test_full_pose_all_testdata_pairs_vs_reference(dvo_mod, testdata_frames, golden_dir):
+    """100 % of the 9 reference pairs within 1e-4 of the REAL reference's pose; sequence API (step)."""
+    m = dvo_mod
+    f = testdata_frames
+    est = _estimator(m, f["K"], f["depth_scale"], 4)
+    est.step(f["bgr"][0], f["depth"][0].copy())
+    rows = []
+    for i in range(1, 10):
+        T = est.step(f["bgr"][i], f["depth"][i].copy())
+        g = np.load(golden_dir / f"pose_testdata_{i}_{i + 1}.npz")
+        dxi = _check_pose(T, g)
+        it = est.last_stats["iters"][0][:4].tolist()
+        rows.append((i, dxi, it, g["iters"].tolist()))
+        np.testing.assert_allclose(est.last_stats["err"][0][:4], g["err_last"], rtol=1e-3)
+    for r in rows:
+        print("pair %d->%d |dxi|max=%.2e iters(cuda)=%s iters(ref)=%s" % (r[0], r[0] + 1, r[1], r[2], r[3]))
+    g = np.load(golden_dir / "pose_testdata_9_10.npz")
+    # pose chaining on the host (current_pose) accumulates nine estimates
+    assert est.current_pose is not None
+
+
+def test_full_pose_variants_vs_reference(dvo_mod, testdata_frames, golden_dir):
+    m = dvo_mod
+    f = testdata_frames
+    for name, kw in (("_tdist", dict(use_weighter=True)), ("_strict", dict(oob_mode="strict"))):
+        est = _estimator(m, f["K"], f["depth_scale"], 4, **kw)
+        est.step(f["bgr"][0], f["depth"][0].copy())
+        T = est.step(f["bgr"][1], f["depth"][1].copy())
+        g = np.load(golden_dir / f"pose_testdata_1_2{name}.npz")
+        print(name, _check_pose(T, g), est.last_stats["iters"][0][:4], g["iters"])
+
+
+def test_sequence_with_prior_vs_reference(dvo_mod, testdata_frames, golden_dir):
+    m = dvo_mod
+    f = testdata_frames
+    g = np.load(golden_dir / "pose_testdata_seq3_sigma.npz")
+    est = _estimator(m, f["K"], f["depth_scale"], 4, sigma=float(g["sigma"]))
+    for i in range(3):
+        T = est.step(f["bgr"][i], f["depth"][i].copy())
+        qt = np.concatenate([T.so3.quat.reshape(4), T.tvec.reshape(3)])
+        assert np.abs(qt - g["qt"][i]).max() < POSE_TOL
+
+
+@pytest.mark.parametrize("name", ["syn160", "syn101", "syn640"])
+def test_batch_aligner_synthetic_vs_reference(dvo_mod, golden_dir, name):
+    """PairBatchAligner on committed synthetic pairs (odd sizes included) against the reference's poses."""
+    import torch
+    m = dvo_mod
+    g = np.load(golden_dir / f"pose_{name}.npz")
+    K = tuple(float(v) for v in g["K"])
+    lv = int(g["levels"])
+    B, h, w = g["gray_prev"].shape
+    cam = m.RGBDCameraModel(_Km(K), float(g["depth_scale"]))
+    al = m.PairBatchAligner(cam, h, w, lv, max_pairs=B)
+    rep = lambda a: np.ascontiguousarray(np.repeat(a[..., None], 3, axis=-1))  # noqa: E731
+    dev = torch.device("cuda", 0)
+    qt, stats = al.align(torch.as_tensor(rep(g["gray_prev"])).to(dev), torch.as_tensor(g["depth_prev"]).to(dev),
+                         torch.as_tensor(rep(g["gray_cur"])).to(dev), torch.as_tensor(g["depth_cur"]).to(dev))
+    for j in range(B):
+        assert np.abs(qt[j, :4] - g[f"p{j}_none_q"]).max() < POSE_TOL
+        assert np.abs(qt[j, 4:] - g[f"p{j}_none_t"]).max() < POSE_TOL
+        print(name, j, "iters", stats["iters"][j][:lv], g[f"p{j}_none_iters"], "flags", stats["flags"][j])
+    # host-buffer (end-to-end) path gives the same answer as the resident path
+    qt2, _ = al.align(rep(g["gray_prev"]), g["depth_prev"].copy(), rep(g["gray_cur"]), g["depth_cur"].copy())
+    np.testing.assert_array_equal(qt, qt2)
+    if name == "syn640":
+        T = m.Se3.from_qt(qt[0])
+        assert np.abs(T.log().reshape(6) - g["xi_true"][0]).max() < 1e-4
+
+
+def test_tdist_batch_vs_reference(dvo_mod, golden_dir):
+    import torch
+    m = dvo_mod
+    g = np.load(golden_dir / "pose_syn160.npz")
+    K = tuple(float(v) for v in g["K"])
+    cam = m.RGBDCameraModel(_Km(K), float(g["depth_scale"]))
+    al = m.PairBatchAligner(cam, 120, 160, 3, max_pairs=1, use_weighter=True)
+    rep = lambda a: np.ascontiguousarray(np.repeat(a[..., None], 3, axis=-1))  # noqa: E731
+    qt, stats = al.align(rep(g["gray_prev"][:1]), g["depth_prev"][:1].copy(), rep(g["gray_cur"][:1]),
+                         g["depth_cur"][:1].copy())
+    assert np.abs(qt[0, :4] - g["p0_tdist_q"]).max() < POSE_TOL
+    assert np.abs(qt[0, 4:] - g["p0_tdist_t"]).max() < POSE_TOL
+
+
+def test_huber_extension_recovers_motion(dvo_mod, golden_dir):
+    """Huber weights are an extension without a reference (parity unpinned): checked against the oracle's
+    restatement of the same definition and against the known synthetic motion."""
+    m = dvo_mod
+    g = np.load(golden_dir / "pose_syn640.npz")
+    K = tuple(float(v) for v in g["K"])
+    Km = _Km(K)
+    cam = m.RGBDCameraModel(Km, float(g["depth_scale"]))
+    al = m.PairBatchAligner(cam, 480, 640, 4, max_pairs=1, weights="huber")
+    rep = lambda a: np.ascontiguousarray(np.repeat(a[..., None], 3, axis=-1))  # noqa: E731
+    qt, stats = al.align(rep(g["gray_prev"][:1]), g["depth_prev"][:1].copy(), rep(g["gray_cur"][:1]),
+                         g["depth_cur"][:1].copy())
+    T = m.Se3.from_qt(qt[0])
+    assert np.abs(T.log().reshape(6) - g["xi_true"][0]).max() < 1e-4
+    res = O.estimate_pose(Km, float(g["depth_scale"]), O.build_pyramid(g["gray_prev"][0], 4),
+                          O.build_pyramid(g["depth_prev"][0], 4), O.build_pyramid(g["gray_cur"][0], 4), 4,
+                          weights=O.W_HUBER)
+    assert np.abs(qt[0, :4] - res.pose.q).max() < POSE_TOL and np.abs(qt[0, 4:] - res.pose.t).max() < POSE_TOL
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+def test_no_valid_depth_returns_initial_guess(dvo_mod):
+    m = dvo_mod
+    cam = m.RGBDCameraModel(_Km((100.0, 100.0, 32.0, 24.0)), 0.001)
+    est = m.get_dvo("robust-dvo", cam, m.Se3.identity(), levels=2)
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (48, 64, 3), dtype=np.uint8)
+    z = np.zeros((48, 64), dtype=np.uint16)
+    est.step(img, z.copy())
+    T = est.step(img, z.copy())
+    # no residuals at all: the reference keeps the estimate (error is NaN, nothing is accepted)
+    assert T is not None and np.allclose(T.exp(), np.eye(4))
+    assert est.last_stats["n_valid"][0][:2].tolist() == [0, 0]
+    assert est.last_stats["flags"][0] & 1
+
+
+def test_identical_frames_give_identity(dvo_mod, golden_dir):
+    m = dvo_mod
+    g = np.load(golden_dir / "pose_syn160.npz")
+    K = tuple(float(v) for v in g["K"])
+    cam = m.RGBDCameraModel(_Km(K), float(g["depth_scale"]))
+    est = m.get_dvo("robust-dvo", cam, m.Se3.identity(), levels=3)
+    c = np.repeat(g["gray_prev"][0][..., None], 3, -1)
+    est.step(c, g["depth_prev"][0].copy())
+    T = est.step(c, g["depth_prev"][0].copy())
+    assert np.abs(T.log()).max() < 1e-6
+
+
+def test_errors_are_loud(dvo_mod):
+    m = dvo_mod
+    cam = m.RGBDCameraModel(np.eye(3, dtype=np.float32), 1.0)
+    with pytest.raises(ValueError):
+        m.get_dvo("kerl", cam, m.Se3.identity(), levels=1)
+    with pytest.raises(ValueError):
+        m.get_dvo("robust-dvo", cam, m.Se3.identity(), levels=0)
+    est = m.get_dvo("robust-dvo", cam, m.Se3.identity(), levels=1)
+    with pytest.raises(NotImplementedError):
+        est._build_pyramids(np.zeros((4, 4), np.uint8), np.zeros((4, 4), np.uint16))
+    est.step(np.zeros((8, 8, 3), np.uint8), np.ones((8, 8), np.uint16))
+    with pytest.raises(ValueError):
+        est.step(np.zeros((9, 8, 3), np.uint8), np.ones((9, 8), np.uint16))
