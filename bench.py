@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""Benchmark of the photometric-alignment hot path (BASELINE.json: pose estimates/s at 640x480, 4 levels).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores
+
+A "step" is one pass of the hot path over one batch of synthetic frame pairs: gray conversion + depth
+clamp + median pyramids + Sobel planes for both frames of every pair, then the full coarse-to-fine
+Gauss-Newton estimate of every pair.  `value` is measured with the frames already resident in HBM; `e2e`
+is the same work through the public API with HOST (pinned) buffers, H2D/D2H inside the timed region.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+H, W, LEVELS = 480, 640, 4
+METRIC = "pose estimates/sec at 640x480, 4-level pyramid"
+UNIT = "pose/s"
+B_PX = 12  # algorithmic bytes per pixel per GN iteration: I1 u8 + D1 u16 + I2 u8 + gx f32 + gy f32
+
+
+def level_pixels():
+    px, h, w = [], H, W
+    for _ in range(LEVELS):
+        px.append(h * w)
+        h, w = (h + 1) // 2, (w + 1) // 2
+    return px
+
+
+# ------------------------------------------------------------------------------------------------ CPU side
+def _cpu_worker(args):
+    """One pose estimate with the oracle port on one process (BLAS pinned to one thread)."""
+    seed, weights = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    os.environ.setdefault("MKL_NUM_THREADS", "1")
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    import dense_visual_odometry_b200  # noqa: F401
+    from dense_visual_odometry_b200.synthetic import make_pairs_numpy
+    from oracle import dvo_oracle as O
+    d = make_pairs_numpy([seed], height=H, width=W)
+    K = d["K"]
+    Km = np.array([[K[0], 0, K[2]], [0, K[1], K[3]], [0, 0, 1]], dtype=np.float32)
+    wmode = {"none": O.W_NONE, "tdist": O.W_TDIST_REF, "huber": O.W_HUBER}[weights]
+    t0 = time.perf_counter()
+    est = O.OracleDVO(Km, d["depth_scale"], LEVELS, weights=wmode)
+    est.step(d["bgr_prev"][0], d["depth_prev"][0].copy())
+    T = est.step(d["bgr_cur"][0], d["depth_cur"][0].copy())
+    dt = time.perf_counter() - t0
+    return seed, np.concatenate([T.q, T.t]).astype(np.float32), dt, est.last_result.iters
+
+
+def cpu_pool(n):
+    import multiprocessing as mp
+    return mp.get_context("spawn").Pool(n)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_cpu_sample(pool, seeds, weights):
+    """Estimates len(seeds) pairs in parallel; returns (pairs/s, results)."""
+    t0 = time.perf_counter()
+    res = pool.map(_cpu_worker, [(s, weights) for s in seeds])
+    dt = time.perf_counter() - t0
+    return len(seeds) / dt, res, dt
+
+
+def reference_arm(args):
+    """--impl reference: the reference algorithm (oracle port; the Python reference itself cannot travel
+    to the GPU box) on all host cores, one pair per process per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    workers = max(1, min(cores, args.cpu_workers or cores))
+    pool = cpu_pool(workers)
+    times = []
+    try:
+        for s in range(args.warmup + args.steps):
+            seeds = [1000 * s + i for i in range(workers)]
+            v, _, dt = run_cpu_sample(pool, seeds, args.weights)
+            if s >= args.warmup:
+                times.append(dt)
+    finally:
+        pool.close()
+    total = sum(times)
+    value = workers * args.steps / total
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "pairs_per_step": workers, "levels": LEVELS,
+                   "weights": args.weights},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
+                         "sample": f"{workers} synthetic 640x480 pairs per step (one per process, BLAS 1 thread each), "
+                                   f"{args.steps} steps; oracle/dvo_oracle.py (NumPy port pinned to the reference)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU side
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in Path(self.f.name).read_text().strip().splitlines() if r.count(",") >= 6]
+        os.unlink(self.f.name)
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                pw.append(float(r[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "power_w_max": max(pw), "samples": len(sm)}
+
+
+def workload_name(args):
+    return (f"batch of independent synthetic 640x480 RGB-D pairs with known SE(3) motion (BASELINE.json configs[1] "
+            f"pair type, batched as configs[3]), {LEVELS}-level pyramid, weights={args.weights}")
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import dense_visual_odometry_b200 as dvo
+    from dense_visual_odometry_b200.synthetic import make_pairs_numpy, make_pairs_torch, TUM_FR1, TUM_DEPTH_SCALE
+
+    B = args.pairs
+    n_cpu = min(args.cpu_pairs, B) if rank == 0 else 0
+    base = rank * B
+    # pairs [0, n_cpu) of rank 0 are rendered with NumPy so the CPU baseline sees bit-identical inputs
+    Km = np.array([[TUM_FR1[0], 0, TUM_FR1[2]], [0, TUM_FR1[1], TUM_FR1[3]], [0, 0, 1]], dtype=np.float32)
+    cam = dvo.RGBDCameraModel(Km, TUM_DEPTH_SCALE)
+    data = make_pairs_torch(range(base, base + B), dev, height=H, width=W)
+    if n_cpu:
+        cpu_data = make_pairs_numpy(range(base, base + n_cpu), height=H, width=W)
+        for k in ("bgr_prev", "depth_prev", "bgr_cur", "depth_cur"):
+            data[k][:n_cpu] = torch.as_tensor(cpu_data[k]).to(dev)
+    bp, dp, bc, dc = data["bgr_prev"], data["depth_prev"], data["bgr_cur"], data["depth_cur"]
+
+    al = dvo.PairBatchAligner(cam, H, W, LEVELS, max_pairs=B, device=local_rank, weights=args.weights,
+                              threads_per_block=args.threads, blocks_per_sm=args.blocks_per_sm,
+                              pixel_batch=args.pixel_batch)
+    gathered = torch.empty((world * B, 7), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step_resident():
+        al.build(bp, dp, bc, dc)
+        qt, st = al.estimate(to_host=False)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, qt.contiguous())
+        return qt, st
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------- device-resident leg -------------------------------------------------------
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = al.launch_count()
+    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        al.build(bp, dp, bc, dc)
+        k_ev[s][0].record()
+        qt, st = al.estimate(to_host=False)
+        k_ev[s][1].record()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, qt.contiguous())
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = al.launch_count() - l0
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * args.steps / (ms_max / 1e3)
+
+    qt_h = qt.cpu().numpy()
+    stats = dvo.stats_to_numpy(st.cpu().numpy())
+    px = level_pixels()
+    iters = stats["iters"][:, :LEVELS].astype(np.int64)
+    algo_bytes = float((iters * np.array(px)[None, :]).sum() * B_PX)
+    extra = 0.0
+    if args.weights == "tdist":   # + the residual pre-pass (4 B/px gathers + 4 B/px store) and one scale pass (4 B/px)
+        extra = float((iters * np.array(px)[None, :]).sum() * 12)
+    peak, peak_src = measured_peak()
+    achieved = (algo_bytes + extra) / (kernel_ms / 1e3) / 1e9
+
+    # ---------------- end-to-end leg: host (pinned) buffers through the public API ----------------
+    hb = [torch.empty(x.shape, dtype=x.dtype).pin_memory() for x in (bp, dp, bc, dc)]
+    for hbuf, x in zip(hb, (bp, dp, bc, dc)):
+        hbuf.copy_(x)
+    torch.cuda.synchronize(dev)
+    for _ in range(max(1, min(args.warmup, 2))):
+        al.align(*hb)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = args.e2e_steps or args.steps
+    for _ in range(e2e_steps):
+        qt_e, st_e = al.align(*hb)       # H2D of all four buffers, kernels, D2H of poses + stats, stream sync
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / float(t.item())
+    h2d = int(sum(x.numel() * x.element_size() for x in hb))
+    d2h = int(B * (7 * 4 + 128))
+    e2e_match = bool(np.array_equal(qt_e, qt_h))
+
+    # ---------------- accuracy of the timed workload + CPU baseline (rank 0) -----------------------
+    xi_true = data["xi"]
+    pose_err = []
+    for j in range(B):
+        T = dvo.Se3.from_qt(qt_h[j])
+        pose_err.append(float(np.abs(T.log().reshape(6) - xi_true[j]).max()))
+    cpu = None
+    parity = None
+    if rank == 0 and n_cpu and not args.no_cpu:
+        cores = host_cores()
+        workers = max(1, min(cores, n_cpu))
+        pool = cpu_pool(workers)
+        try:
+            run_cpu_sample(pool, [base + i for i in range(workers)], args.weights)       # warm the workers
+            v, res, dt = run_cpu_sample(pool, [base + i for i in range(n_cpu)], args.weights)
+        finally:
+            pool.close()
+        dmax = max(float(np.abs(r[1] - qt_h[r[0] - base]).max()) for r in res)
+        parity = {"pairs": n_cpu, "max_abs_pose_diff_vs_oracle": dmax, "tolerance": 1e-4, "ok": dmax < 1e-4}
+        cpu = {"value": v, "unit": UNIT, "cores": workers, "kind": "port",
+               "sample": f"{n_cpu} of the timed pairs (seeds {base}..{base + n_cpu - 1}), one process per pair, BLAS 1 "
+                         f"thread each, {dt:.1f} s wall; oracle/dvo_oracle.py (NumPy port pinned to the reference)"}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "pairs_per_gpu": B, "global_pairs": world * B,
+                       "levels": LEVELS, "weights": args.weights, "parallelism": f"pairs sharded over {world} GPU(s)",
+                       "l2_policy": "inputs larger than L2 (%.2f GB of frames + %.2f GB of pyramids per GPU)" % (
+                           4 * B * H * W * 2.5 / 2 / 1e9, 2 * B * 4.5e6 / 1e9),
+                       "threads_per_block": args.threads or 256, "pixel_batch": args.pixel_batch or 2},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "align_kernel", "kernel_ms": kernel_ms,
+                         "algorithmic_bytes_per_launch": algo_bytes + extra, "peak_source": peak_src,
+                         "gn_iterations_per_pose_mean": float(iters.sum(1).mean())},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "matches_resident": e2e_match},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "accuracy": {"max_abs_twist_error_vs_truth": float(np.max(pose_err)),
+                         "frac_within_1e-4": float(np.mean(np.array(pose_err) < 1e-4)),
+                         "flags_nonzero": int((stats["flags"] != 0).sum())},
+            "parity": parity,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=512, help="frame pairs per GPU per step")
+    ap.add_argument("--weights", default="none", choices=["none", "tdist", "huber"])
+    ap.add_argument("--cpu-pairs", type=int, default=8, help="pairs of the batch also estimated by the CPU oracle")
+    ap.add_argument("--cpu-workers", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0)
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--blocks-per-sm", type=int, default=0)
+    ap.add_argument("--pixel-batch", type=int, default=0)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -82,10 +82,10 @@ extern "C" const char* dvo_last_error(const dvo_handle* h) { return h ? h->err.c
 // ---- kernel dispatch ---------------------------------------------------------------------------
 typedef void (*align_fn)(const AlignParams);
 
-template <int T, int B>
+template <int T, int B, int NB>
 static align_fn pick_align(int w, int oob) {
 #define DVO_PICK(WM, OM) \
-    if (w == WM && oob == OM) return (align_fn)align_kernel<WM, OM, T, B>;
+    if (w == WM && oob == OM) return (align_fn)align_kernel<WM, OM, T, B, NB>;
     DVO_PICK(DVO_W_NONE, DVO_OOB_INCLUSIVE)
     DVO_PICK(DVO_W_NONE, DVO_OOB_STRICT)
     DVO_PICK(DVO_W_TDIST_REF, DVO_OOB_INCLUSIVE)
@@ -97,9 +97,14 @@ static align_fn pick_align(int w, int oob) {
 }
 
 static align_fn get_align(const dvo_handle* h) {
-    if (h->threads == 512) return pick_align<512, 1>(h->cfg.weights, h->cfg.oob_mode);
-    if (h->threads == 128) return pick_align<128, 4>(h->cfg.weights, h->cfg.oob_mode);
-    return pick_align<256, 2>(h->cfg.weights, h->cfg.oob_mode);
+    // reserved[0] selects the pixel batch per gather phase (2 or 4) for tuning experiments
+    const bool nb4 = h->cfg.reserved[0] == 4;
+    if (h->threads == 512) return nb4 ? pick_align<512, 1, 4>(h->cfg.weights, h->cfg.oob_mode)
+                                      : pick_align<512, 1, 2>(h->cfg.weights, h->cfg.oob_mode);
+    if (h->threads == 128) return nb4 ? pick_align<128, 4, 4>(h->cfg.weights, h->cfg.oob_mode)
+                                      : pick_align<128, 4, 2>(h->cfg.weights, h->cfg.oob_mode);
+    return nb4 ? pick_align<256, 2, 4>(h->cfg.weights, h->cfg.oob_mode)
+               : pick_align<256, 2, 2>(h->cfg.weights, h->cfg.oob_mode);
 }
 
 typedef void (*dump_fn)(const AlignParams, int, int, int, const float*, float, float*, float*, uint8_t*, uint8_t*,
