@@ -25,7 +25,7 @@ struct dvo_handle {
     size_t lplane[DVO_MAX_LEVELS]{};
     uint8_t* gray[DVO_MAX_LEVELS]{};
     uint16_t* depth[DVO_MAX_LEVELS]{};
-    float2* grad[DVO_MAX_LEVELS]{};
+    float4* rec[DVO_MAX_LEVELS]{};
     float k4[DVO_MAX_LEVELS][4]{}, kinv4[DVO_MAX_LEVELS][4]{};
     int* queue = nullptr;
     float* scratch = nullptr;
@@ -82,10 +82,10 @@ extern "C" const char* dvo_last_error(const dvo_handle* h) { return h ? h->err.c
 // ---- kernel dispatch ---------------------------------------------------------------------------
 typedef void (*align_fn)(const AlignParams);
 
-template <int T, int B, int NB>
+template <int T, int B, int NP>
 static align_fn pick_align(int w, int oob) {
 #define DVO_PICK(WM, OM) \
-    if (w == WM && oob == OM) return (align_fn)align_kernel<WM, OM, T, B, NB>;
+    if (w == WM && oob == OM) return (align_fn)align_kernel<WM, OM, T, B, NP>;
     DVO_PICK(DVO_W_NONE, DVO_OOB_INCLUSIVE)
     DVO_PICK(DVO_W_NONE, DVO_OOB_STRICT)
     DVO_PICK(DVO_W_TDIST_REF, DVO_OOB_INCLUSIVE)
@@ -96,15 +96,17 @@ static align_fn pick_align(int w, int oob) {
     return nullptr;
 }
 
+// Launch shapes: threads per CTA x CTAs per SM (register budget = 65536 / (threads * CTAs)).
 static align_fn get_align(const dvo_handle* h) {
-    // reserved[0] selects the pixel batch per gather phase (2 or 4) for tuning experiments
-    const bool nb4 = h->cfg.reserved[0] == 4;
-    if (h->threads == 512) return nb4 ? pick_align<512, 1, 4>(h->cfg.weights, h->cfg.oob_mode)
-                                      : pick_align<512, 1, 2>(h->cfg.weights, h->cfg.oob_mode);
-    if (h->threads == 128) return nb4 ? pick_align<128, 4, 4>(h->cfg.weights, h->cfg.oob_mode)
-                                      : pick_align<128, 4, 2>(h->cfg.weights, h->cfg.oob_mode);
-    return nb4 ? pick_align<256, 2, 4>(h->cfg.weights, h->cfg.oob_mode)
-               : pick_align<256, 2, 2>(h->cfg.weights, h->cfg.oob_mode);
+    const int w = h->cfg.weights, o = h->cfg.oob_mode;
+    const bool two = h->cfg.blocks_per_sm == 2;
+    switch (h->threads) {
+        case 128: return two ? pick_align<128, 2, 1>(w, o) : pick_align<128, 3, 1>(w, o);
+        case 192: return pick_align<192, 2, 1>(w, o);
+        case 384: return pick_align<384, 1, 1>(w, o);
+        case 512: return pick_align<512, 1, 1>(w, o);
+        default: return pick_align<256, 1, 1>(w, o);
+    }
 }
 
 typedef void (*dump_fn)(const AlignParams, int, int, int, const float*, float, float*, float*, uint8_t*, uint8_t*,
@@ -132,7 +134,7 @@ extern "C" int dvo_destroy(dvo_handle* h) {
     for (int l = 0; l < DVO_MAX_LEVELS; ++l) {
         cudaFree(h->gray[l]);
         cudaFree(h->depth[l]);
-        cudaFree(h->grad[l]);
+        cudaFree(h->rec[l]);
     }
     cudaFree(h->queue);
     cudaFree(h->scratch);
@@ -163,16 +165,26 @@ static int create_impl(dvo_handle* h) {
         const size_t n = h->lplane[l] * h->max_frames;
         DVO_CUDA(h, cudaMalloc(&h->gray[l], n));
         DVO_CUDA(h, cudaMalloc(&h->depth[l], n * sizeof(uint16_t)));
-        DVO_CUDA(h, cudaMalloc(&h->grad[l], n * sizeof(float2)));
+        DVO_CUDA(h, cudaMalloc(&h->rec[l], n * sizeof(float4)));
         DVO_CUDA(h, cudaMemset(h->gray[l], 0, n));
         DVO_CUDA(h, cudaMemset(h->depth[l], 0, n * sizeof(uint16_t)));
-        DVO_CUDA(h, cudaMemset(h->grad[l], 0, n * sizeof(float2)));
+        DVO_CUDA(h, cudaMemset(h->rec[l], 0, n * sizeof(float4)));
+        {   // row = umulhi(e, floor(2^32/pitch)+1) must be exact for every element of the plane
+            const unsigned magic = (unsigned)((1ull << 32) / (unsigned)h->lpitch[l]) + 1u;
+            for (int r = 1; r <= hh; ++r) {
+                const unsigned long long e1 = (unsigned long long)r * h->lpitch[l] - 1, e2 = e1 + 1;
+                if ((unsigned)((e1 * magic) >> 32) != (unsigned)(r - 1) || (r < hh && (unsigned)((e2 * magic) >> 32) != (unsigned)r)) {
+                    h->err = "image too large for the 32-bit row index arithmetic";
+                    return DVO_ERR_INVALID;
+                }
+            }
+        }
         w = (w + 1) / 2;   // image_pyramid.py:21 / :84-85 (ceil division)
         hh = (hh + 1) / 2;
     }
     h->threads = h->cfg.threads_per_block ? h->cfg.threads_per_block : 256;
-    if (h->threads != 128 && h->threads != 256 && h->threads != 512) {
-        h->err = "threads_per_block must be 0, 128, 256 or 512";
+    if (h->threads != 128 && h->threads != 192 && h->threads != 256 && h->threads != 384 && h->threads != 512) {
+        h->err = "threads_per_block must be 0, 128, 192, 256, 384 or 512";
         return DVO_ERR_INVALID;
     }
     align_fn fn = get_align(h);
@@ -294,7 +306,7 @@ static int build_levels(dvo_handle* h, int frame_base, int n_frames, int with_gr
         for (int l = 0; l < h->levels; ++l) {
             dim3 grid((h->lw[l] + 255) / 256, h->lh[l], n_frames);
             sobel3_kernel<<<grid, 256, 0, st>>>(h->gray[l] + (size_t)frame_base * h->lplane[l],
-                                                h->grad[l] + (size_t)frame_base * h->lplane[l], h->lw[l], h->lh[l],
+                                                h->rec[l] + (size_t)frame_base * h->lplane[l], h->lw[l], h->lh[l],
                                                 h->lpitch[l], h->lplane[l]);
             h->launches += 1;
         }
@@ -371,7 +383,7 @@ extern "C" int dvo_get_pyramid(dvo_handle* h, int slot, int level, uint8_t* gray
     const size_t off = (size_t)slot * h->lplane[level];
     if (gray_dev) unpitch_kernel<uint8_t><<<grid, 256, 0, st>>>(h->gray[level] + off, gray_dev, w, hh, pitch);
     if (depth_dev) unpitch_kernel<uint16_t><<<grid, 256, 0, st>>>(h->depth[level] + off, depth_dev, w, hh, pitch);
-    if (gx_dev || gy_dev) unpitch_grad_kernel<<<grid, 256, 0, st>>>(h->grad[level] + off, gx_dev, gy_dev, w, hh, pitch);
+    if (gx_dev || gy_dev) unpitch_grad_kernel<<<grid, 256, 0, st>>>(h->rec[level] + off, gx_dev, gy_dev, w, hh, pitch);
     h->launches += (gray_dev != nullptr) + (depth_dev != nullptr) + ((gx_dev || gy_dev) ? 1 : 0);
     DVO_CUDA(h, cudaGetLastError());
     return DVO_OK;
@@ -384,12 +396,13 @@ static void fill_params(const dvo_handle* h, AlignParams& p) {
         LevelGeom& g = p.lv[l];
         g.gray = h->gray[l];
         g.depth = h->depth[l];
-        g.grad = h->grad[l];
+        g.rec = h->rec[l];
         g.plane = h->lplane[l];
         g.w = h->lw[l];
         g.h = h->lh[l];
         g.pitch = h->lpitch[l];
-        g.n_groups = (int)(h->lplane[l] / 4);
+        g.n_tiles = (int)((h->lplane[l] + 127) / 128);
+        g.div_magic = (unsigned)((1ull << 32) / (unsigned)h->lpitch[l]) + 1u;
         g.fx = h->k4[l][0]; g.fy = h->k4[l][1]; g.cx = h->k4[l][2]; g.cy = h->k4[l][3];
         g.ifx = h->kinv4[l][0]; g.ify = h->kinv4[l][1]; g.icx = h->kinv4[l][2]; g.icy = h->kinv4[l][3];
     }
@@ -409,6 +422,7 @@ static void fill_params(const dvo_handle* h, AlignParams& p) {
     p.queue = h->queue;
     p.scratch = h->scratch;
     p.scratch_stride = h->scratch_stride;
+    p.prefetch_mode = h->cfg.reserved[1];
 }
 
 extern "C" int dvo_estimate(dvo_handle* h, int prev_base, int cur_base, int n_pairs, const float* init_qt_dev,
@@ -488,12 +502,12 @@ extern "C" int dvo_residuals_jacobian(dvo_handle* h, int prev_slot, int cur_slot
     pose_matrix_kernel<<<1, 1, 0, st>>>(h->qt_one, h->qt_one + 16);
     if (acc_dev) DVO_CUDA(h, cudaMemsetAsync(acc_dev, 0, sizeof(double) * DVO_ACC_TERMS, st));
     dump_fn fn = get_dump(h);
-    const int n_groups = (int)(h->lplane[level] / 4);
+    const int n_tiles = (int)((h->lplane[level] + 127) / 128);
     const float* T12 = h->qt_one + 16;
     float lambda = 0.0f;
     void* args[] = {&p, &level, &prev_slot, &cur_slot, &T12, &lambda, &r_dev, &J_dev, &depth_mask_dev,
                     &warp_valid_dev, &acc_dev};
-    DVO_CUDA(h, cudaLaunchKernel((const void*)fn, dim3((n_groups + 255) / 256), dim3(256), args, 0, st));
+    DVO_CUDA(h, cudaLaunchKernel((const void*)fn, dim3((n_tiles + 7) / 8), dim3(256), args, 0, st));
     h->launches += 2;
     return DVO_OK;
 }
