@@ -216,7 +216,7 @@ def gpu_arm(args):
 
     al = dvo.PairBatchAligner(cam, H, W, LEVELS, max_pairs=B, device=local_rank, weights=args.weights,
                               threads_per_block=args.threads, blocks_per_sm=args.blocks_per_sm,
-                              pixel_batch=args.pixel_batch, prefetch_mode=args.prefetch)
+                              pixel_batch=args.pixel_batch, prefetch_mode=args.prefetch, prefetch_rows=args.prefetch_rows)
     gathered = torch.empty((world * B, 7), dtype=torch.float32, device=dev) if world > 1 else None
 
     def step_resident():
@@ -360,6 +360,7 @@ def main():
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--pixel-batch", type=int, default=0)
     ap.add_argument("--prefetch", type=int, default=0)
+    ap.add_argument("--prefetch-rows", type=int, default=0)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -82,31 +82,31 @@ extern "C" const char* dvo_last_error(const dvo_handle* h) { return h ? h->err.c
 // ---- kernel dispatch ---------------------------------------------------------------------------
 typedef void (*align_fn)(const AlignParams);
 
-template <int T, int B, int NP>
+template <int T, int B>
 static align_fn pick_align(int w, int oob) {
 #define DVO_PICK(WM, OM) \
-    if (w == WM && oob == OM) return (align_fn)align_kernel<WM, OM, T, B, NP>;
+    if (w == WM && oob == OM) return (align_fn)align_kernel<WM, OM, T, B>;
     DVO_PICK(DVO_W_NONE, DVO_OOB_INCLUSIVE)
+#ifndef DVO_FAST_BUILD
     DVO_PICK(DVO_W_NONE, DVO_OOB_STRICT)
     DVO_PICK(DVO_W_TDIST_REF, DVO_OOB_INCLUSIVE)
     DVO_PICK(DVO_W_TDIST_REF, DVO_OOB_STRICT)
     DVO_PICK(DVO_W_HUBER, DVO_OOB_INCLUSIVE)
     DVO_PICK(DVO_W_HUBER, DVO_OOB_STRICT)
+#endif
 #undef DVO_PICK
     return nullptr;
 }
 
-// Launch shapes: threads per CTA x CTAs per SM (register budget = 65536 / (threads * CTAs)).
+// Launch shapes: threads per CTA x minimum CTAs per SM (register budget = 65536 / (threads * CTAs)).
+// Default: 128 threads x 2 CTAs per SM, so one CTA's reduction / solve overlaps the other's streaming.
 static align_fn get_align(const dvo_handle* h) {
     const int w = h->cfg.weights, o = h->cfg.oob_mode;
-    const bool two = h->cfg.blocks_per_sm == 2;
-    switch (h->threads) {
-        case 128: return two ? pick_align<128, 2, 1>(w, o) : pick_align<128, 3, 1>(w, o);
-        case 192: return pick_align<192, 2, 1>(w, o);
-        case 384: return pick_align<384, 1, 1>(w, o);
-        case 512: return pick_align<512, 1, 1>(w, o);
-        default: return pick_align<256, 1, 1>(w, o);
-    }
+    const int b = h->cfg.blocks_per_sm;
+    if (h->threads == 256) return pick_align<256, 1>(w, o);
+    if (h->threads == 384) return pick_align<384, 1>(w, o);
+    if (h->threads == 512) return pick_align<512, 1>(w, o);
+    return b == 3 ? pick_align<128, 3>(w, o) : pick_align<128, 2>(w, o);
 }
 
 typedef void (*dump_fn)(const AlignParams, int, int, int, const float*, float, float*, float*, uint8_t*, uint8_t*,
@@ -160,21 +160,31 @@ static int create_impl(dvo_handle* h) {
     for (int l = 0; l < h->levels; ++l) {
         h->lw[l] = w;
         h->lh[l] = hh;
-        h->lpitch[l] = (w + 15) & ~15;
+        h->lpitch[l] = (w + kTile - 1) / kTile * kTile;
         h->lplane[l] = (size_t)hh * h->lpitch[l];
+        // tap indices travel as 2^23 + index in a float32 (align_kernel.cuh, prep_pair)
+        if (h->lplane[l] + (size_t)h->lpitch[l] + 2 >= (1u << 23)) {
+            h->err = "image too large: a level plane must hold fewer than 2^23 pixels";
+            return DVO_ERR_INVALID;
+        }
         const size_t n = h->lplane[l] * h->max_frames;
-        DVO_CUDA(h, cudaMalloc(&h->gray[l], n));
-        DVO_CUDA(h, cudaMalloc(&h->depth[l], n * sizeof(uint16_t)));
-        DVO_CUDA(h, cudaMalloc(&h->rec[l], n * sizeof(float4)));
-        DVO_CUDA(h, cudaMemset(h->gray[l], 0, n));
-        DVO_CUDA(h, cudaMemset(h->depth[l], 0, n * sizeof(uint16_t)));
-        DVO_CUDA(h, cudaMemset(h->rec[l], 0, n * sizeof(float4)));
-        {   // row = umulhi(e, floor(2^32/pitch)+1) must be exact for every element of the plane
-            const unsigned magic = (unsigned)((1ull << 32) / (unsigned)h->lpitch[l]) + 1u;
-            for (int r = 1; r <= hh; ++r) {
-                const unsigned long long e1 = (unsigned long long)r * h->lpitch[l] - 1, e2 = e1 + 1;
-                if ((unsigned)((e1 * magic) >> 32) != (unsigned)(r - 1) || (r < hh && (unsigned)((e2 * magic) >> 32) != (unsigned)r)) {
-                    h->err = "image too large for the 32-bit row index arithmetic";
+        // the unclamped +1 taps of the last row of the last frame read up to pitch + 1 records past the end
+        const size_t n_rec = n + 34 * (size_t)h->lpitch[l];
+        // the align kernel prefetches previous-frame samples up to two tiles past a warp's range
+        const size_t n_raw = n + 35 * (size_t)h->lpitch[l];
+        DVO_CUDA(h, cudaMalloc(&h->gray[l], n_raw));
+        DVO_CUDA(h, cudaMalloc(&h->depth[l], n_raw * sizeof(uint16_t)));
+        DVO_CUDA(h, cudaMalloc(&h->rec[l], n_rec * sizeof(float4)));
+        DVO_CUDA(h, cudaMemset(h->gray[l], 0, n_raw));
+        DVO_CUDA(h, cudaMemset(h->depth[l], 0, n_raw * sizeof(uint16_t)));
+        DVO_CUDA(h, cudaMemset(h->rec[l], 0, n_rec * sizeof(float4)));
+        {   // strip = umulhi(t, floor(2^32/h)+1) must be exact for every tile index of the plane
+            const unsigned magic = (unsigned)((1ull << 32) / (unsigned)hh) + 1u;
+            const int strips = h->lpitch[l] / kTile;
+            for (int s = 1; s <= strips; ++s) {
+                const unsigned long long t1 = (unsigned long long)s * hh - 1, t2 = t1 + 1;
+                if ((unsigned)((t1 * magic) >> 32) != (unsigned)(s - 1) || (s < strips && (unsigned)((t2 * magic) >> 32) != (unsigned)s)) {
+                    h->err = "image too large for the 32-bit tile index arithmetic";
                     return DVO_ERR_INVALID;
                 }
             }
@@ -182,9 +192,9 @@ static int create_impl(dvo_handle* h) {
         w = (w + 1) / 2;   // image_pyramid.py:21 / :84-85 (ceil division)
         hh = (hh + 1) / 2;
     }
-    h->threads = h->cfg.threads_per_block ? h->cfg.threads_per_block : 256;
-    if (h->threads != 128 && h->threads != 192 && h->threads != 256 && h->threads != 384 && h->threads != 512) {
-        h->err = "threads_per_block must be 0, 128, 192, 256, 384 or 512";
+    h->threads = h->cfg.threads_per_block ? h->cfg.threads_per_block : 128;
+    if (h->threads != 128 && h->threads != 256 && h->threads != 384 && h->threads != 512) {
+        h->err = "threads_per_block must be 0, 128, 256, 384 or 512";
         return DVO_ERR_INVALID;
     }
     align_fn fn = get_align(h);
@@ -401,8 +411,9 @@ static void fill_params(const dvo_handle* h, AlignParams& p) {
         g.w = h->lw[l];
         g.h = h->lh[l];
         g.pitch = h->lpitch[l];
-        g.n_tiles = (int)((h->lplane[l] + 127) / 128);
-        g.div_magic = (unsigned)((1ull << 32) / (unsigned)h->lpitch[l]) + 1u;
+        g.strips = h->lpitch[l] / kTile;
+        g.n_tiles = g.strips * h->lh[l];
+        g.h_magic = (unsigned)((1ull << 32) / (unsigned)h->lh[l]) + 1u;
         g.fx = h->k4[l][0]; g.fy = h->k4[l][1]; g.cx = h->k4[l][2]; g.cy = h->k4[l][3];
         g.ifx = h->kinv4[l][0]; g.ify = h->kinv4[l][1]; g.icx = h->kinv4[l][2]; g.icy = h->kinv4[l][3];
     }
@@ -423,6 +434,7 @@ static void fill_params(const dvo_handle* h, AlignParams& p) {
     p.scratch = h->scratch;
     p.scratch_stride = h->scratch_stride;
     p.prefetch_mode = h->cfg.reserved[1];
+    p.prefetch_rows = h->cfg.reserved[2] > 0 ? h->cfg.reserved[2] : 4;
 }
 
 extern "C" int dvo_estimate(dvo_handle* h, int prev_base, int cur_base, int n_pairs, const float* init_qt_dev,
@@ -502,7 +514,7 @@ extern "C" int dvo_residuals_jacobian(dvo_handle* h, int prev_slot, int cur_slot
     pose_matrix_kernel<<<1, 1, 0, st>>>(h->qt_one, h->qt_one + 16);
     if (acc_dev) DVO_CUDA(h, cudaMemsetAsync(acc_dev, 0, sizeof(double) * DVO_ACC_TERMS, st));
     dump_fn fn = get_dump(h);
-    const int n_tiles = (int)((h->lplane[level] + 127) / 128);
+    const int n_tiles = (int)(h->lplane[level] / kTile);
     const float* T12 = h->qt_one + 16;
     float lambda = 0.0f;
     void* args[] = {&p, &level, &prev_slot, &cur_slot, &T12, &lambda, &r_dev, &J_dev, &depth_mask_dev,
