@@ -359,7 +359,7 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--pixel-batch", type=int, default=0)
-    ap.add_argument("--prefetch", type=int, default=0)
+    ap.add_argument("--prefetch", type=int, default=-1)
     ap.add_argument("--prefetch-rows", type=int, default=0)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

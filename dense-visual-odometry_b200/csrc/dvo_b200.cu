@@ -25,7 +25,7 @@ struct dvo_handle {
     size_t lplane[DVO_MAX_LEVELS]{};
     uint8_t* gray[DVO_MAX_LEVELS]{};
     uint16_t* depth[DVO_MAX_LEVELS]{};
-    float4* rec[DVO_MAX_LEVELS]{};
+    uint2* rec[DVO_MAX_LEVELS]{};
     float k4[DVO_MAX_LEVELS][4]{}, kinv4[DVO_MAX_LEVELS][4]{};
     int* queue = nullptr;
     float* scratch = nullptr;
@@ -174,10 +174,10 @@ static int create_impl(dvo_handle* h) {
         const size_t n_raw = n + 35 * (size_t)h->lpitch[l];
         DVO_CUDA(h, cudaMalloc(&h->gray[l], n_raw));
         DVO_CUDA(h, cudaMalloc(&h->depth[l], n_raw * sizeof(uint16_t)));
-        DVO_CUDA(h, cudaMalloc(&h->rec[l], n_rec * sizeof(float4)));
+        DVO_CUDA(h, cudaMalloc(&h->rec[l], n_rec * sizeof(uint2)));
         DVO_CUDA(h, cudaMemset(h->gray[l], 0, n_raw));
         DVO_CUDA(h, cudaMemset(h->depth[l], 0, n_raw * sizeof(uint16_t)));
-        DVO_CUDA(h, cudaMemset(h->rec[l], 0, n_rec * sizeof(float4)));
+        DVO_CUDA(h, cudaMemset(h->rec[l], 0, n_rec * sizeof(uint2)));
         {   // strip = umulhi(t, floor(2^32/h)+1) must be exact for every tile index of the plane
             const unsigned magic = (unsigned)((1ull << 32) / (unsigned)hh) + 1u;
             const int strips = h->lpitch[l] / kTile;
@@ -414,6 +414,13 @@ static void fill_params(const dvo_handle* h, AlignParams& p) {
         g.strips = h->lpitch[l] / kTile;
         g.n_tiles = g.strips * h->lh[l];
         g.h_magic = (unsigned)((1ull << 32) / (unsigned)h->lh[l]) + 1u;
+        {   // chunks per strip = NW * k with about 30 rows per chunk (align_kernel.cuh, fused_pass)
+            const int nw = h->threads / 32;
+            int k = (h->lh[l] + nw * 15) / (nw * 30);
+            if (k < 1) k = 1;
+            g.chunks_per_strip = nw * k;
+            g.chunk_rows = (h->lh[l] + g.chunks_per_strip - 1) / g.chunks_per_strip;
+        }
         g.fx = h->k4[l][0]; g.fy = h->k4[l][1]; g.cx = h->k4[l][2]; g.cy = h->k4[l][3];
         g.ifx = h->kinv4[l][0]; g.ify = h->kinv4[l][1]; g.icx = h->kinv4[l][2]; g.icy = h->kinv4[l][3];
     }
@@ -433,8 +440,9 @@ static void fill_params(const dvo_handle* h, AlignParams& p) {
     p.queue = h->queue;
     p.scratch = h->scratch;
     p.scratch_stride = h->scratch_stride;
-    p.prefetch_mode = h->cfg.reserved[1];
-    p.prefetch_rows = h->cfg.reserved[2] > 0 ? h->cfg.reserved[2] : 4;
+    // tuning knobs (dvo_config.reserved[1..2]); defaults: L1 prefetch by cp.async touch, two rows ahead
+    p.prefetch_mode = h->cfg.reserved[1] > 0 ? h->cfg.reserved[1] - 1 : 3;
+    p.prefetch_rows = h->cfg.reserved[2] > 0 ? h->cfg.reserved[2] : 2;
 }
 
 extern "C" int dvo_estimate(dvo_handle* h, int prev_base, int cur_base, int n_pairs, const float* init_qt_dev,

@@ -4,9 +4,9 @@
 //                         (reference: core/base_dense_visual_odometry.py:58-59)
 //   median3_down_kernel   3x3 median, replicated border, keep even rows/cols
 //                         (reference: utils/image_pyramid.py:19-21, cv2.medianBlur(.,3)[::2, ::2])
-//   sobel3_kernel         3x3 Sobel dx/dy, gain 8, replicated border -> float4 records {gx, gy, I, 0}
-//                         (reference: utils/jacobian.py:70-71); the intensity rides along so that one
-//                         16-byte load per bilinear tap feeds the alignment kernel
+//   sobel3_kernel         3x3 Sobel dx/dy, gain 8, replicated border -> packed 8-byte records {gx, gy, I}
+//                         (reference: utils/jacobian.py:70-71; layout: rec_pack in align_kernel.cuh); the
+//                         intensity rides along so that one 8-byte load per bilinear tap feeds the alignment kernel
 //
 // Plane layout: every level plane is [frame][h][pitch] with pitch a multiple of 16 elements; padding
 // columns stay zero (the planes are cleared once at creation and kernels only write col < w), so a
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) median3_down_kernel(const T* __restrict__
 }
 
 // ---- a9 -----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sobel3_kernel(const uint8_t* __restrict__ gray, float4* __restrict__ rec,
+__global__ void __launch_bounds__(256) sobel3_kernel(const uint8_t* __restrict__ gray, uint2* __restrict__ rec,
                                                      int w, int h, int pitch, size_t plane) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256) sobel3_kernel(const uint8_t* __restrict__
     const int a20 = __ldg(r2 + xm), a21 = __ldg(r2 + x), a22 = __ldg(r2 + xp);
     const int gx = (a02 + 2 * a12 + a22) - (a00 + 2 * a10 + a20);
     const int gy = (a20 + 2 * a21 + a22) - (a00 + 2 * a01 + a02);
-    rec[(size_t)frame * plane + (size_t)y * pitch + x] = make_float4((float)gx, (float)gy, (float)a11, 0.0f);
+    rec[(size_t)frame * plane + (size_t)y * pitch + x] = rec_pack(gx, gy, a11);
 }
 
 // Dense read-back of one level plane (drops the pitch padding); used by dvo_get_pyramid.
@@ -166,14 +166,15 @@ __global__ void unpitch_kernel(const T* __restrict__ src, T* __restrict__ dst, i
     const int y = blockIdx.y;
     if (x < w) dst[(size_t)y * w + x] = src[(size_t)y * pitch + x];
 }
-__global__ void unpitch_grad_kernel(const float4* __restrict__ src, float* __restrict__ gx, float* __restrict__ gy,
+__global__ void unpitch_grad_kernel(const uint2* __restrict__ src, float* __restrict__ gx, float* __restrict__ gy,
                                     int w, int h, int pitch) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     if (x < w) {
-        const float4 g = src[(size_t)y * pitch + x];
-        if (gx) gx[(size_t)y * w + x] = g.x;
-        if (gy) gy[(size_t)y * w + x] = g.y;
+        int a, b, c;
+        rec_unpack(src[(size_t)y * pitch + x], a, b, c);
+        if (gx) gx[(size_t)y * w + x] = (float)a;
+        if (gy) gy[(size_t)y * w + x] = (float)b;
     }
 }
 

@@ -93,7 +93,7 @@ class _Handle:
 
 def make_config(use_weighter=False, max_increased_steps_allowed=0, sigma=None, tolerance=1e-6, max_iterations=100,
                 weights: Optional[str] = None, oob_mode="inclusive", huber_k=None, max_distance=5.0,
-                threads_per_block=0, blocks_per_sm=0, pixel_batch=0, prefetch_mode=0, prefetch_rows=0):
+                threads_per_block=0, blocks_per_sm=0, pixel_batch=0, prefetch_mode=-1, prefetch_rows=0):
     lib = _cabi.load()
     cfg = _cabi.dvo_config()
     lib.dvo_default_config(C.byref(cfg))
@@ -115,7 +115,8 @@ def make_config(use_weighter=False, max_increased_steps_allowed=0, sigma=None, t
     cfg.threads_per_block = int(threads_per_block)
     cfg.blocks_per_sm = int(blocks_per_sm)
     cfg.reserved[0] = int(pixel_batch)   # unused tuning knob
-    cfg.reserved[1] = int(prefetch_mode)  # tuning knob: 0 none, 1 L1, 2 L2, 3 bulk-L2 prefetch ahead of the strip walk
+    # tuning knob: -1 library default, 0 none, 1 prefetch.global.L1, 2 prefetch.global.L2, 3 cp.async touch (L1)
+    cfg.reserved[1] = int(prefetch_mode) + 1
     cfg.reserved[2] = int(prefetch_rows)  # rows ahead (<= 32)
     return cfg
 

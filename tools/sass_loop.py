@@ -21,11 +21,11 @@ for a, t in ins:
 best = None
 for lo, hi in loops:
     body = [t for a, t in ins if lo <= a <= hi]
-    n128 = sum("LDG.E.128" in t for t in body)
+    n128 = sum(("LDG.E.128" in t) or ("LDG.E.64" in t) for t in body)
     if n128 >= 8 and (best is None or len(body) < best[2]):
         best = (lo, hi, len(body), body)
 lo, hi, n, body = best
-print(f"{f.splitlines()[0].strip()}\nloop 0x{lo:x}..0x{hi:x}: {n} instructions, {sum('LDG.E.128' in t for t in body)} LDG.128")
+print(f"{f.splitlines()[0].strip()}\nloop 0x{lo:x}..0x{hi:x}: {n} instructions, {sum(("LDG.E.128" in t) or ("LDG.E.64" in t) for t in body)} wide LDG")
 h = collections.Counter()
 for t in body:
     t = re.sub(r"^@!?U?P\d+\s+", "", t)
