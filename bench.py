@@ -216,14 +216,14 @@ def gpu_arm(args):
 
     al = dvo.PairBatchAligner(cam, H, W, LEVELS, max_pairs=B, device=local_rank, weights=args.weights,
                               threads_per_block=args.threads, blocks_per_sm=args.blocks_per_sm,
-                              pixel_batch=args.pixel_batch, prefetch_mode=args.prefetch, prefetch_rows=args.prefetch_rows)
-    gathered = torch.empty((world * B, 7), dtype=torch.float32, device=dev) if world > 1 else None
+                              prefetch_mode=args.prefetch, prefetch_rows=args.prefetch_rows)
+    from dense_visual_odometry_b200.sharding import gather_poses
 
     def step_resident():
         al.build(bp, dp, bc, dc)
         qt, st = al.estimate(to_host=False)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, qt.contiguous())
+            gather_poses(qt, world * B)   # the path's only collective: [B,7] poses per rank (NCCL)
         return qt, st
 
     def barrier():
@@ -246,7 +246,7 @@ def gpu_arm(args):
         qt, st = al.estimate(to_host=False)
         k_ev[s][1].record()
         if world > 1:
-            dist.all_gather_into_tensor(gathered, qt.contiguous())
+            gather_poses(qt, world * B)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -323,8 +323,8 @@ def gpu_arm(args):
             "config": {"workload": workload_name(args), "pairs_per_gpu": B, "global_pairs": world * B,
                        "levels": LEVELS, "weights": args.weights, "parallelism": f"pairs sharded over {world} GPU(s)",
                        "l2_policy": "inputs larger than L2 (%.2f GB of frames + %.2f GB of pyramids per GPU)" % (
-                           4 * B * H * W * 2.5 / 2 / 1e9, 2 * B * 4.5e6 / 1e9),
-                       "threads_per_block": args.threads or 256, "pixel_batch": args.pixel_batch or 2},
+                           2 * B * H * W * 5 / 1e9, 2 * B * 437760 * 11 / 1e9),
+                       "threads_per_block": args.threads or 128},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "align_kernel", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": algo_bytes + extra, "peak_source": peak_src,
@@ -350,7 +350,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pairs", type=int, default=512, help="frame pairs per GPU per step")
+    ap.add_argument("--pairs", type=int, default=4096, help="frame pairs per GPU per step (BASELINE.json configs[3])")
     ap.add_argument("--weights", default="none", choices=["none", "tdist", "huber"])
     ap.add_argument("--cpu-pairs", type=int, default=8, help="pairs of the batch also estimated by the CPU oracle")
     ap.add_argument("--cpu-workers", type=int, default=0)
@@ -358,7 +358,6 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--blocks-per-sm", type=int, default=0)
-    ap.add_argument("--pixel-batch", type=int, default=0)
     ap.add_argument("--prefetch", type=int, default=-1)
     ap.add_argument("--prefetch-rows", type=int, default=0)
     args = ap.parse_args()

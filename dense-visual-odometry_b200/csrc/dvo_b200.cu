@@ -27,7 +27,8 @@ struct dvo_handle {
     uint16_t* depth[DVO_MAX_LEVELS]{};
     uint2* rec[DVO_MAX_LEVELS]{};
     float k4[DVO_MAX_LEVELS][4]{}, kinv4[DVO_MAX_LEVELS][4]{};
-    int* queue = nullptr;
+    int* queue = nullptr;   // kQueueSlots pair counters; concurrent dvo_estimate calls (different streams) rotate through them
+    int queue_next = 0;
     float* scratch = nullptr;
     size_t scratch_stride = 0;
     int sm_count = 0, threads = 256, blocks_per_sm = 2, grid_max = 0;
@@ -44,6 +45,8 @@ struct dvo_handle {
     std::string err;
 };
 
+static const int kQueueSlots = 256;
+static const int kScratchSets = 3;  // t-distribution residual planes for up to 3 estimate launches in flight
 static const char* kNullHandle = "null handle";
 
 #define DVO_CUDA(h, call)                                                                             \
@@ -207,10 +210,10 @@ static int create_impl(dvo_handle* h) {
     if (occ < 1) occ = 1;
     h->blocks_per_sm = h->cfg.blocks_per_sm > 0 ? (h->cfg.blocks_per_sm < occ ? h->cfg.blocks_per_sm : occ) : occ;
     h->grid_max = h->sm_count * h->blocks_per_sm;
-    DVO_CUDA(h, cudaMalloc(&h->queue, sizeof(int)));
+    DVO_CUDA(h, cudaMalloc(&h->queue, sizeof(int) * kQueueSlots));
     if (h->cfg.weights == DVO_W_TDIST_REF) {
         h->scratch_stride = h->lplane[0];
-        DVO_CUDA(h, cudaMalloc(&h->scratch, h->scratch_stride * sizeof(float) * (size_t)h->grid_max));
+        DVO_CUDA(h, cudaMalloc(&h->scratch, h->scratch_stride * sizeof(float) * (size_t)h->grid_max * kScratchSets));
     }
     DVO_CUDA(h, cudaMalloc(&h->qt_init, sizeof(float) * 7 * h->max_pairs));
     DVO_CUDA(h, cudaMalloc(&h->qt_last, sizeof(float) * 7 * h->max_pairs));
@@ -464,7 +467,10 @@ extern "C" int dvo_estimate(dvo_handle* h, int prev_base, int cur_base, int n_pa
     p.last_qt = last_qt_dev;
     p.out_qt = out_qt_dev;
     p.stats = stats_dev;
-    DVO_CUDA(h, cudaMemsetAsync(h->queue, 0, sizeof(int), st));
+    p.queue = h->queue + h->queue_next;
+    if (h->scratch) p.scratch = h->scratch + (size_t)(h->queue_next % kScratchSets) * h->scratch_stride * (size_t)h->grid_max;
+    h->queue_next = (h->queue_next + 1) % (kQueueSlots / kScratchSets * kScratchSets);
+    DVO_CUDA(h, cudaMemsetAsync(p.queue, 0, sizeof(int), st));
     const int grid = n_pairs < h->grid_max ? n_pairs : h->grid_max;
     align_fn fn = get_align(h);
     DVO_CUDA(h, cudaEventRecord(h->ev0, st));

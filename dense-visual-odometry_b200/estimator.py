@@ -93,7 +93,7 @@ class _Handle:
 
 def make_config(use_weighter=False, max_increased_steps_allowed=0, sigma=None, tolerance=1e-6, max_iterations=100,
                 weights: Optional[str] = None, oob_mode="inclusive", huber_k=None, max_distance=5.0,
-                threads_per_block=0, blocks_per_sm=0, pixel_batch=0, prefetch_mode=-1, prefetch_rows=0):
+                threads_per_block=0, blocks_per_sm=0, prefetch_mode=-1, prefetch_rows=0):
     lib = _cabi.load()
     cfg = _cabi.dvo_config()
     lib.dvo_default_config(C.byref(cfg))
@@ -114,7 +114,6 @@ def make_config(use_weighter=False, max_increased_steps_allowed=0, sigma=None, t
     cfg.max_distance = float(max_distance)
     cfg.threads_per_block = int(threads_per_block)
     cfg.blocks_per_sm = int(blocks_per_sm)
-    cfg.reserved[0] = int(pixel_batch)   # unused tuning knob
     # tuning knob: -1 library default, 0 none, 1 prefetch.global.L1, 2 prefetch.global.L2, 3 cp.async touch (L1)
     cfg.reserved[1] = int(prefetch_mode) + 1
     cfg.reserved[2] = int(prefetch_rows)  # rows ahead (<= 32)
@@ -379,15 +378,19 @@ class PairBatchAligner:
             raise ValueError(f"batch {B} exceeds max_pairs {self.max_pairs}")
         st = _stream_ptr(torch, self._dev)
         if isinstance(bgr_prev, np.ndarray) or not bgr_prev.is_cuda:
-            as_t = (lambda a: torch.as_tensor(a)) if isinstance(bgr_prev, np.ndarray) else (lambda a: a)
-            bp, dp, bc, dc = (as_t(a).contiguous() for a in (bgr_prev, depth_prev, bgr_cur, depth_cur))
-            self._keep = (bp, dp, bc, dc)
+            bp, dp, bc, dc = self._as_host_tensors(bgr_prev, depth_prev, bgr_cur, depth_cur)
             self._h.call("dvo_build_pyramids_host", 0, self._ptr(bp), self._ptr(dp), B, 0, st)
             self._h.call("dvo_build_pyramids_host", self.max_pairs, self._ptr(bc), self._ptr(dc), B, 1, st)
         else:
             self._h.call("dvo_build_pyramids", 0, self._ptr(bgr_prev), self._ptr(depth_prev), B, 0, st)
             self._h.call("dvo_build_pyramids", self.max_pairs, self._ptr(bgr_cur), self._ptr(depth_cur), B, 1, st)
         self._B = B
+
+    def _as_host_tensors(self, *arrays):
+        torch = self._torch
+        out = tuple((torch.as_tensor(a) if isinstance(a, np.ndarray) else a).contiguous() for a in arrays)
+        self._keep = out  # the copies are asynchronous: keep the sources alive
+        return out
 
     def estimate(self, init_qt=None, to_host: bool = True):
         """Runs the GN kernel on the pairs of the last build().  Returns (qt [B,7], stats dict) as host arrays
@@ -408,9 +411,46 @@ class PairBatchAligner:
         torch.cuda.current_stream(self._dev).synchronize()
         return self._pin_qt[:B].numpy().copy(), stats_to_numpy(self._pin_stats[:B].numpy())
 
-    def align(self, bgr_prev, depth_prev, bgr_cur, depth_cur, init_qt=None):
-        self.build(bgr_prev, depth_prev, bgr_cur, depth_cur)
-        return self.estimate(init_qt)
+    def align(self, bgr_prev, depth_prev, bgr_cur, depth_cur, init_qt=None, chunk_pairs: int = 256):
+        """build() + estimate().  Host inputs are pipelined: the batch is cut into chunks of `chunk_pairs` pairs
+        that go round-robin over three streams, so the host->device copy of a chunk overlaps the pyramids and the
+        Gauss-Newton kernel of the chunks before it (kernels of different chunks share the GPU).  The result does
+        not depend on the chunking: every pair is estimated by one CTA with a fixed order of operations."""
+        host = isinstance(bgr_prev, np.ndarray) or not bgr_prev.is_cuda
+        B = bgr_prev.shape[0]
+        if not host or B <= chunk_pairs:
+            self.build(bgr_prev, depth_prev, bgr_cur, depth_cur)
+            return self.estimate(init_qt)
+        torch = self._torch
+        if B > self.max_pairs:
+            raise ValueError(f"batch {B} exceeds max_pairs {self.max_pairs}")
+        bp, dp, bc, dc = self._as_host_tensors(bgr_prev, depth_prev, bgr_cur, depth_cur)
+        init_dev = None
+        if init_qt is not None:
+            init_dev = torch.as_tensor(np.asarray(init_qt, dtype=np.float32)).to(self._dev).contiguous()
+            self._init = init_dev
+        if not hasattr(self, "_streams"):
+            self._streams = [torch.cuda.Stream(self._dev) for _ in range(3)]
+        cur = torch.cuda.current_stream(self._dev)
+        for s in self._streams:
+            s.wait_stream(cur)
+        for k, lo in enumerate(range(0, B, chunk_pairs)):
+            n = min(chunk_pairs, B - lo)
+            s = self._streams[k % 3]
+            sp = C.c_void_p(s.cuda_stream)
+            self._h.call("dvo_build_pyramids_host", lo, self._ptr(bp[lo]), self._ptr(dp[lo]), n, 0, sp)
+            self._h.call("dvo_build_pyramids_host", self.max_pairs + lo, self._ptr(bc[lo]), self._ptr(dc[lo]), n, 1, sp)
+            init_ptr = self._ptr(init_dev[lo]) if init_dev is not None else None
+            self._h.call("dvo_estimate", lo, self.max_pairs + lo, n, init_ptr, None, self._ptr(self._qt[lo]),
+                         self._ptr(self._stats[lo]), sp)
+            with torch.cuda.stream(s):
+                self._pin_qt[lo:lo + n].copy_(self._qt[lo:lo + n], non_blocking=True)
+                self._pin_stats[lo:lo + n].copy_(self._stats[lo:lo + n], non_blocking=True)
+        for s in self._streams:
+            s.synchronize()
+            cur.wait_stream(s)
+        self._B = B
+        return self._pin_qt[:B].numpy().copy(), stats_to_numpy(self._pin_stats[:B].numpy())
 
     def last_kernel_ms(self) -> float:
         return self._h.last_estimate_ms()

@@ -128,6 +128,9 @@ int dvo_depth_clamp_threshold(const dvo_handle* h, int* threshold);
  *   stats_dev    [n] dvo_pair_stats or NULL */
 int dvo_estimate(dvo_handle* h, int prev_base, int cur_base, int n_pairs, const float* init_qt_dev,
                  const float* last_qt_dev, float* out_qt_dev, dvo_pair_stats* stats_dev, void* stream);
+/* Calls on DIFFERENT streams may be in flight together (a caller pipelining host->device copies of the
+ * next pairs behind the estimate of the previous ones): use at most 3 streams, round-robin, and disjoint
+ * frame slots / output ranges per call. */
 /* Same, results copied to host memory (pinned => asynchronous); waits for nothing. */
 int dvo_estimate_host(dvo_handle* h, int prev_base, int cur_base, int n_pairs, const float* init_qt_host,
                       const float* last_qt_host, float* out_qt_host, dvo_pair_stats* stats_host, void* stream);

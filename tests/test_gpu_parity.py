@@ -280,6 +280,11 @@ def test_batch_aligner_synthetic_vs_reference(dvo_mod, golden_dir, name):
     # host-buffer (end-to-end) path gives the same answer as the resident path
     qt2, _ = al.align(rep(g["gray_prev"]), g["depth_prev"].copy(), rep(g["gray_cur"]), g["depth_cur"].copy())
     np.testing.assert_array_equal(qt, qt2)
+    # the pipelined host path (chunks on three streams, one launch per chunk) is chunking-independent
+    qt3, st3 = al.align(rep(g["gray_prev"]), g["depth_prev"].copy(), rep(g["gray_cur"]), g["depth_cur"].copy(),
+                        chunk_pairs=1)
+    np.testing.assert_array_equal(qt, qt3)
+    np.testing.assert_array_equal(stats["iters"], st3["iters"])
     if name == "syn640":
         T = m.Se3.from_qt(qt[0])
         assert np.abs(T.log().reshape(6) - g["xi_true"][0]).max() < 1e-4
