@@ -216,7 +216,7 @@ def gpu_arm(args):
 
     al = dvo.PairBatchAligner(cam, H, W, LEVELS, max_pairs=B, device=local_rank, weights=args.weights,
                               threads_per_block=args.threads, blocks_per_sm=args.blocks_per_sm,
-                              prefetch_mode=args.prefetch, prefetch_rows=args.prefetch_rows)
+                              prefetch_rows=args.prefetch_rows)
     from dense_visual_odometry_b200.sharding import gather_poses
 
     def step_resident():
@@ -358,7 +358,6 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--blocks-per-sm", type=int, default=0)
-    ap.add_argument("--prefetch", type=int, default=-1)
     ap.add_argument("--prefetch-rows", type=int, default=0)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

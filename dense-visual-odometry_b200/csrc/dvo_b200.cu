@@ -443,9 +443,8 @@ static void fill_params(const dvo_handle* h, AlignParams& p) {
     p.queue = h->queue;
     p.scratch = h->scratch;
     p.scratch_stride = h->scratch_stride;
-    // tuning knobs (dvo_config.reserved[1..2]); defaults: L1 prefetch by cp.async touch, two rows ahead
-    p.prefetch_mode = h->cfg.reserved[1] > 0 ? h->cfg.reserved[1] - 1 : 3;
-    p.prefetch_rows = h->cfg.reserved[2] > 0 ? h->cfg.reserved[2] : 2;
+    // tuning knob (dvo_config.reserved[2]): L1 prefetch distance in rows; 0 = default (2), < 0 = off
+    p.prefetch_rows = h->cfg.reserved[2] > 0 ? h->cfg.reserved[2] : (h->cfg.reserved[2] < 0 ? 0 : 2);
 }
 
 extern "C" int dvo_estimate(dvo_handle* h, int prev_base, int cur_base, int n_pairs, const float* init_qt_dev,

@@ -93,7 +93,7 @@ class _Handle:
 
 def make_config(use_weighter=False, max_increased_steps_allowed=0, sigma=None, tolerance=1e-6, max_iterations=100,
                 weights: Optional[str] = None, oob_mode="inclusive", huber_k=None, max_distance=5.0,
-                threads_per_block=0, blocks_per_sm=0, prefetch_mode=-1, prefetch_rows=0):
+                threads_per_block=0, blocks_per_sm=0, prefetch_rows=0):
     lib = _cabi.load()
     cfg = _cabi.dvo_config()
     lib.dvo_default_config(C.byref(cfg))
@@ -114,9 +114,7 @@ def make_config(use_weighter=False, max_increased_steps_allowed=0, sigma=None, t
     cfg.max_distance = float(max_distance)
     cfg.threads_per_block = int(threads_per_block)
     cfg.blocks_per_sm = int(blocks_per_sm)
-    # tuning knob: -1 library default, 0 none, 1 prefetch.global.L1, 2 prefetch.global.L2, 3 cp.async touch (L1)
-    cfg.reserved[1] = int(prefetch_mode) + 1
-    cfg.reserved[2] = int(prefetch_rows)  # rows ahead (<= 32)
+    cfg.reserved[2] = int(prefetch_rows)  # tuning knob: L1 prefetch distance in rows (0 = default, < 0 = off, <= 32)
     return cfg
 
 
