@@ -417,9 +417,9 @@ static void fill_params(const dvo_handle* h, AlignParams& p) {
         g.strips = h->lpitch[l] / kTile;
         g.n_tiles = g.strips * h->lh[l];
         g.h_magic = (unsigned)((1ull << 32) / (unsigned)h->lh[l]) + 1u;
-        {   // chunks per strip = NW * k with about 30 rows per chunk (align_kernel.cuh, fused_pass)
+        {   // chunks per strip = NW * k with about 60 rows per chunk (align_kernel.cuh, fused_pass)
             const int nw = h->threads / 32;
-            int k = (h->lh[l] + nw * 15) / (nw * 30);
+            int k = (h->lh[l] + nw * 30) / (nw * 60);
             if (k < 1) k = 1;
             g.chunks_per_strip = nw * k;
             g.chunk_rows = (h->lh[l] + g.chunks_per_strip - 1) / g.chunks_per_strip;

@@ -457,6 +457,85 @@ class PairBatchAligner:
         return self._h.launch_count()
 
 
+class SequenceAligner:
+    """A stream of N frames -> N-1 relative poses in one go (BASELINE.json configs[2]).
+
+    Frame f lives in frame slot f and its pyramids and gradient planes are built ONCE; pair p aligns slot p
+    (previous frame) against slot p+1 (current frame), i.e. `dvo_estimate(prev_base=0, cur_base=1)`.  Every pair
+    starts from the identity guess exactly as `step()` does (base_dense_visual_odometry.py:56,67), so the pairs
+    are independent and run as one batch; the `sigma` motion prior would make them serially dependent and is
+    rejected here (use RobustDVOB200.step for that).  Host inputs are pipelined over three streams like
+    PairBatchAligner.align."""
+
+    def __init__(self, camera_model, height: int, width: int, levels: int, max_frames: int, device: int = 0,
+                 **cfg_kwargs):
+        if cfg_kwargs.get("sigma") is not None:
+            raise ValueError("the sigma prior couples consecutive pairs; use RobustDVOB200.step()")
+        torch = _torch()
+        self._torch = torch
+        self._dev = torch.device("cuda", device)
+        self.max_frames = int(max_frames)
+        self.levels = int(levels)
+        if self.max_frames < 2:
+            raise ValueError("a sequence needs at least two frames")
+        self._cfg = make_config(**cfg_kwargs)
+        self._h = _Handle(device, height, width, levels, self.max_frames, self.max_frames - 1, self._cfg)
+        fx, fy, cx, cy, scale = _intrinsics_of(camera_model)
+        self._h.call("dvo_set_intrinsics", fx, fy, cx, cy, scale)
+        n = self.max_frames - 1
+        self._qt = torch.empty((n, 7), dtype=torch.float32, device=self._dev)
+        self._stats = torch.empty((n, _cabi.STATS_BYTES), dtype=torch.uint8, device=self._dev)
+        self._pin_qt = torch.empty((n, 7), dtype=torch.float32).pin_memory()
+        self._pin_stats = torch.empty((n, _cabi.STATS_BYTES), dtype=torch.uint8).pin_memory()
+        self._streams = [torch.cuda.Stream(self._dev) for _ in range(3)]
+
+    @property
+    def handle(self) -> _Handle:
+        return self._h
+
+    def align(self, bgr, depth, chunk_frames: int = 256):
+        """bgr [N,H,W,3] u8, depth [N,H,W] u16 (host arrays / pinned tensors or CUDA tensors).
+        Returns (qt [N-1,7], stats dict) as host arrays; qt[p] takes frame p's camera to frame p+1's."""
+        torch = self._torch
+        N = bgr.shape[0]
+        if N < 2 or N > self.max_frames:
+            raise ValueError(f"need 2..{self.max_frames} frames, got {N}")
+        host = isinstance(bgr, np.ndarray) or not bgr.is_cuda
+        if host:
+            bgr = (torch.as_tensor(bgr) if isinstance(bgr, np.ndarray) else bgr).contiguous()
+            depth = (torch.as_tensor(depth) if isinstance(depth, np.ndarray) else depth).contiguous()
+            self._keep = (bgr, depth)
+        build = "dvo_build_pyramids_host" if host else "dvo_build_pyramids"
+        cur = torch.cuda.current_stream(self._dev)
+        for s in self._streams:
+            s.wait_stream(cur)
+        built = None  # event: the previous chunk's pyramids are complete
+        for k, lo in enumerate(range(0, N, chunk_frames)):
+            hi = min(lo + chunk_frames, N)
+            s = self._streams[k % 3]
+            sp = C.c_void_p(s.cuda_stream)
+            self._h.call(build, lo, C.c_void_p(bgr[lo].data_ptr()), C.c_void_p(depth[lo].data_ptr()), hi - lo, 1, sp)
+            ev = torch.cuda.Event()
+            ev.record(s)
+            p0, p1 = max(lo - 1, 0), hi - 1   # pairs whose current frame is in this chunk
+            if p1 > p0:
+                if built is not None and p0 < lo:
+                    s.wait_event(built)       # pair lo-1 reads frame lo-1, built on another stream
+                self._h.call("dvo_estimate", p0, p0 + 1, p1 - p0, None, None, C.c_void_p(self._qt[p0].data_ptr()),
+                             C.c_void_p(self._stats[p0].data_ptr()), sp)
+                with torch.cuda.stream(s):
+                    self._pin_qt[p0:p1].copy_(self._qt[p0:p1], non_blocking=True)
+                    self._pin_stats[p0:p1].copy_(self._stats[p0:p1], non_blocking=True)
+            built = ev
+        for s in self._streams:
+            s.synchronize()
+            cur.wait_stream(s)
+        return self._pin_qt[:N - 1].numpy().copy(), stats_to_numpy(self._pin_stats[:N - 1].numpy())
+
+    def launch_count(self) -> int:
+        return self._h.launch_count()
+
+
 def robust_dvo_factory(use_gpu: bool = True, **kwargs):
     """Mirror of core/robust_dense_visual_odometry/__init__.py:5-25 with the B200 backend as the GPU branch.
     There is no CPU branch here: `use_gpu=False` is an error, not a fallback."""

@@ -365,3 +365,97 @@ def test_errors_are_loud(dvo_mod):
     est.step(np.zeros((8, 8, 3), np.uint8), np.ones((8, 8), np.uint16))
     with pytest.raises(ValueError):
         est.step(np.zeros((9, 8, 3), np.uint8), np.ones((9, 8), np.uint16))
+
+
+# ------------------------------------------------------------------------------------------------ sequences
+def test_sequence_aligner_vs_reference_and_step(dvo_mod, testdata_frames, golden_dir):
+    """BASELINE.json configs[2] shape: one batch call over a frame stream (each pyramid built once, pair p =
+    slots p, p+1) gives the REAL reference's pose for every pair and exactly what step() gives; chunked host
+    pipelining (cross-stream dependency on the shared frame) does not change a bit."""
+    m = dvo_mod
+    f = testdata_frames
+    cam = m.RGBDCameraModel(_Km(f["K"]), f["depth_scale"])
+    seq = m.SequenceAligner(cam, 480, 640, 4, max_frames=10)
+    bgr = np.stack(f["bgr"][:10])
+    depth = np.stack([d.copy() for d in f["depth"][:10]])
+    qt, stats = seq.align(bgr, depth)
+    assert qt.shape == (9, 7)
+    for i in range(1, 10):
+        g = np.load(golden_dir / f"pose_testdata_{i}_{i + 1}.npz")
+        assert np.abs(qt[i - 1, :4] - g["q"].reshape(4)).max() < POSE_TOL
+        assert np.abs(qt[i - 1, 4:] - g["t"].reshape(3)).max() < POSE_TOL
+    qt2, stats2 = seq.align(bgr, depth, chunk_frames=3)
+    np.testing.assert_array_equal(qt, qt2)
+    np.testing.assert_array_equal(stats["iters"], stats2["iters"])
+    est = _estimator(m, f["K"], f["depth_scale"], 4)
+    est.step(f["bgr"][0], f["depth"][0].copy())
+    T = est.step(f["bgr"][1], f["depth"][1].copy())
+    np.testing.assert_array_equal(qt[0], m.pose_to_qt(T))
+    # absolute trajectory by the reference's chaining rule
+    traj = m.chain_poses(qt)
+    g = np.load(golden_dir / "pose_testdata_9_10.npz")
+    assert len(traj) == 10 and np.all(np.isfinite(m.pose_to_qt(traj[-1])))
+    with pytest.raises(ValueError):
+        m.SequenceAligner(cam, 480, 640, 4, max_frames=10, sigma=1.0)
+
+
+def test_sequence_aligner_tdist_synthetic(dvo_mod):
+    """t-distribution weights over a three-frame synthetic stream (prev, cur, prev again): both pairs match the
+    oracle run pair by pair."""
+    from dense_visual_odometry_b200.synthetic import make_pairs_numpy
+    m = dvo_mod
+    d = make_pairs_numpy([3], height=120, width=160)
+    K = d["K"]
+    cam = m.RGBDCameraModel(_Km(K), d["depth_scale"])
+    bgr = np.stack([d["bgr_prev"][0], d["bgr_cur"][0], d["bgr_prev"][0]])
+    dep = np.stack([d["depth_prev"][0], d["depth_cur"][0], d["depth_prev"][0]])
+    seq = m.SequenceAligner(cam, 120, 160, 3, max_frames=3, use_weighter=True)
+    qt, stats = seq.align(bgr, dep.copy())
+    for p in range(2):
+        ref = O.OracleDVO(_Km(K), d["depth_scale"], 3, weights=O.W_TDIST_REF)
+        ref.step(bgr[p], dep[p].copy())
+        Tr = ref.step(bgr[p + 1], dep[p + 1].copy())
+        assert np.abs(qt[p, :4] - Tr.q).max() < POSE_TOL and np.abs(qt[p, 4:] - Tr.t).max() < POSE_TOL
+
+
+# ------------------------------------------------------------------------------------------------ large frames
+@pytest.mark.parametrize("hw", [(720, 1280), (1080, 1920)])
+def test_high_resolution_five_levels(dvo_mod, hw):
+    """BASELINE.json configs[4], photometric part: 1280x720 and 1920x1080 pairs, 5-level pyramid: the full pose
+    against the oracle (the reference's termination rule stops well short of the true motion on these scenes, so
+    the truth is not the yardstick), bit-exact pyramids, and per-pixel r / J / the fused sums of the coarsest
+    and the finest level against the oracle."""
+    from dense_visual_odometry_b200.synthetic import make_pairs_numpy, TUM_FR1
+    m = dvo_mod
+    h, w = hw
+    s = w / 640.0
+    K = (TUM_FR1[0] * s, TUM_FR1[1] * s, TUM_FR1[2] * s, TUM_FR1[3] * s)
+    d = make_pairs_numpy([5], height=h, width=w, K=K)
+    Km = _Km(K)
+    cam = m.RGBDCameraModel(Km, d["depth_scale"])
+    est = m.get_dvo("robust-dvo", cam, m.Se3.identity(), levels=5)
+    est.step(d["bgr_prev"][0], d["depth_prev"][0].copy())
+    T = est.step(d["bgr_cur"][0], d["depth_cur"][0].copy())
+    assert T is not None and est.last_stats["flags"][0] == 0
+    ref = O.OracleDVO(Km, d["depth_scale"], 5)
+    ref.step(d["bgr_prev"][0], d["depth_prev"][0].copy())
+    Tr = ref.step(d["bgr_cur"][0], d["depth_cur"][0].copy())
+    print("iters", est.last_stats["iters"][0][:5].tolist(), ref.last_result.iters)
+    assert np.abs(T.so3.quat.reshape(4) - Tr.q).max() < POSE_TOL
+    assert np.abs(T.tvec.reshape(3) - Tr.t).max() < POSE_TOL
+    gp, gc = O.bgr_to_gray(d["bgr_prev"][0]), O.bgr_to_gray(d["bgr_cur"][0])
+    dp = O.clamp_depth(d["depth_prev"][0], d["depth_scale"])
+    pg, pd, cg = O.build_pyramid(gp, 5), O.build_pyramid(dp, 5), O.build_pyramid(gc, 5)
+    est = m.get_dvo("robust-dvo", cam, m.Se3.identity(), levels=5)   # hooks: previous frame = the stored one
+    est.step(d["bgr_prev"][0], d["depth_prev"][0].copy())
+    est._build_pyramids(gc, O.clamp_depth(d["depth_cur"][0], d["depth_scale"]))
+    report = {}
+    for lv in (4, 0):
+        g_, d_, gx_, gy_ = est.get_pyramid_level(est._hook_slots[1], lv)
+        np.testing.assert_array_equal(g_, cg[lv])
+        ogx, ogy = O.sobel3(cg[lv])
+        np.testing.assert_array_equal(gx_, ogx)
+        np.testing.assert_array_equal(gy_, ogy)
+        ld = O.prepare_level(Km, d["depth_scale"], pg[lv], pd[lv], cg[lv], lv)
+        _compare_level(est, m, ld, m.Se3.identity(), lv, O.OOB_INCLUSIVE, report)
+    print("high-res dense parity:", hw, report)

@@ -1,6 +1,5 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-for cfg in "--pairs 2048 --threads 256" "--pairs 2048 --threads 128"; do
-python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1 $cfg 2>&1 | tail -1 | python -c "
+for cfg in "--threads 128" "--threads 256"; do
+python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1 --pairs 2048 $cfg 2>&1 | tail -1 | python -c "
 import sys,json
 for l in sys.stdin:
     if l.startswith('{'):
