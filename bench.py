@@ -184,6 +184,15 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic_per_pair():
+    """DRAM bytes per frame pair of align_kernel from the committed ncu capture (profiles/r1/ncu_traffic.json)."""
+    p = ROOT / "profiles" / "r1" / "ncu_traffic.json"
+    try:
+        return float(json.loads(p.read_text())["dram_bytes_per_pair"])
+    except Exception:
+        return None
+
+
 def gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -202,7 +211,7 @@ def gpu_arm(args):
     from dense_visual_odometry_b200.synthetic import make_pairs_numpy, make_pairs_torch, TUM_FR1, TUM_DEPTH_SCALE
 
     B = args.pairs
-    n_cpu = min(args.cpu_pairs, B) if rank == 0 else 0
+    n_cpu = min(args.cpu_pairs or min(host_cores(), 32), B) if rank == 0 else 0
     base = rank * B
     # pairs [0, n_cpu) of rank 0 are rendered with NumPy so the CPU baseline sees bit-identical inputs
     Km = np.array([[TUM_FR1[0], 0, TUM_FR1[2]], [0, TUM_FR1[1], TUM_FR1[3]], [0, 0, 1]], dtype=np.float32)
@@ -326,7 +335,10 @@ def gpu_arm(args):
                            2 * B * H * W * 5 / 1e9, 2 * B * 437760 * 11 / 1e9),
                        "threads_per_block": args.threads or 128},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "align_kernel", "kernel_ms": kernel_ms,
+                         "traffic": (ncu_traffic_per_pair() * B / 1e9) if (ncu_traffic_per_pair() and args.weights == "none") else None,
+                         "traffic_note": "GB per launch: dram__bytes_read+write per pair from the ncu --set full capture "
+                                         "(profiles/r1/ncu_traffic.json, 1184 pairs) x pairs in this launch",
+                         "kernel": "align_kernel", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": algo_bytes + extra, "peak_source": peak_src,
                          "gn_iterations_per_pose_mean": float(iters.sum(1).mean())},
             "cpu_baseline": cpu,
@@ -352,7 +364,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=4096, help="frame pairs per GPU per step (BASELINE.json configs[3])")
     ap.add_argument("--weights", default="none", choices=["none", "tdist", "huber"])
-    ap.add_argument("--cpu-pairs", type=int, default=8, help="pairs of the batch also estimated by the CPU oracle")
+    ap.add_argument("--cpu-pairs", type=int, default=0,
+                    help="pairs of the batch also estimated by the CPU oracle (0 = one per host core, at most 32)")
     ap.add_argument("--cpu-workers", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0)

@@ -101,15 +101,13 @@ static align_fn pick_align(int w, int oob) {
     return nullptr;
 }
 
-// Launch shapes: threads per CTA x minimum CTAs per SM (register budget = 65536 / (threads * CTAs)).
-// Default: 128 threads x 2 CTAs per SM, so one CTA's reduction / solve overlaps the other's streaming.
+// Launch shapes: 128 threads x 2 CTAs per SM (default: one CTA's reduction / solve overlaps the other's streaming)
+// or 256 threads x 1 CTA per SM (lower latency for a single pair).  Both run 8 warps per SM at 255 registers;
+// shapes with more warps per SM spill inside the pipelined loop and measured slower (profiles/r1/SUMMARY.md).
 static align_fn get_align(const dvo_handle* h) {
     const int w = h->cfg.weights, o = h->cfg.oob_mode;
-    const int b = h->cfg.blocks_per_sm;
     if (h->threads == 256) return pick_align<256, 1>(w, o);
-    if (h->threads == 384) return pick_align<384, 1>(w, o);
-    if (h->threads == 512) return pick_align<512, 1>(w, o);
-    return b == 3 ? pick_align<128, 3>(w, o) : pick_align<128, 2>(w, o);
+    return pick_align<128, 2>(w, o);
 }
 
 typedef void (*dump_fn)(const AlignParams, int, int, int, const float*, float, float*, float*, uint8_t*, uint8_t*,
@@ -196,8 +194,8 @@ static int create_impl(dvo_handle* h) {
         hh = (hh + 1) / 2;
     }
     h->threads = h->cfg.threads_per_block ? h->cfg.threads_per_block : 128;
-    if (h->threads != 128 && h->threads != 256 && h->threads != 384 && h->threads != 512) {
-        h->err = "threads_per_block must be 0, 128, 256, 384 or 512";
+    if (h->threads != 128 && h->threads != 256) {
+        h->err = "threads_per_block must be 0, 128 or 256";
         return DVO_ERR_INVALID;
     }
     align_fn fn = get_align(h);

@@ -153,8 +153,9 @@ class RobustDVOB200:
         self._sigma = sigma
         self._max_distance = max_distance
         self._device = device
+        # one pair at a time: a 256-thread CTA (8 warps on the pair) halves the latency of the 128-thread default
         self._cfg = make_config(use_weighter, max_increased_steps_allowed, sigma, tolerance, max_iterations, weights,
-                                oob_mode, huber_k, max_distance)
+                                oob_mode, huber_k, max_distance, threads_per_block=256)
         self._h: Optional[_Handle] = None
         self._have_prev = False
         self._prev_slot = 0           # step(): slot holding the previous frame

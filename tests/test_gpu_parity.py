@@ -390,7 +390,8 @@ def test_sequence_aligner_vs_reference_and_step(dvo_mod, testdata_frames, golden
     est = _estimator(m, f["K"], f["depth_scale"], 4)
     est.step(f["bgr"][0], f["depth"][0].copy())
     T = est.step(f["bgr"][1], f["depth"][1].copy())
-    np.testing.assert_array_equal(qt[0], m.pose_to_qt(T))
+    # step() runs the 256-thread CTA shape: same arithmetic, different order of the partial sums
+    np.testing.assert_allclose(qt[0], m.pose_to_qt(T), atol=5e-6)
     # absolute trajectory by the reference's chaining rule
     traj = m.chain_poses(qt)
     g = np.load(golden_dir / "pose_testdata_9_10.npz")
