@@ -44,7 +44,7 @@ def level_pixels():
 # ------------------------------------------------------------------------------------------------ CPU side
 def _cpu_worker(args):
     """One pose estimate with the oracle port on one process (BLAS pinned to one thread)."""
-    seed, weights = args
+    seed, weights, approx = args
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
     os.environ.setdefault("MKL_NUM_THREADS", "1")
@@ -61,7 +61,7 @@ def _cpu_worker(args):
     Km = np.array([[K[0], 0, K[2]], [0, K[1], K[3]], [0, 0, 1]], dtype=np.float32)
     wmode = {"none": O.W_NONE, "tdist": O.W_TDIST_REF, "huber": O.W_HUBER}[weights]
     t0 = time.perf_counter()
-    est = O.OracleDVO(Km, d["depth_scale"], LEVELS, weights=wmode)
+    est = O.OracleDVO(Km, d["depth_scale"], LEVELS, weights=wmode, approximate_image2_gradient=approx)
     est.step(d["bgr_prev"][0], d["depth_prev"][0].copy())
     T = est.step(d["bgr_cur"][0], d["depth_cur"][0].copy())
     dt = time.perf_counter() - t0
@@ -80,10 +80,10 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def run_cpu_sample(pool, seeds, weights):
+def run_cpu_sample(pool, seeds, weights, approx=False):
     """Estimates len(seeds) pairs in parallel; returns (pairs/s, results)."""
     t0 = time.perf_counter()
-    res = pool.map(_cpu_worker, [(s, weights) for s in seeds])
+    res = pool.map(_cpu_worker, [(s, weights, approx) for s in seeds])
     dt = time.perf_counter() - t0
     return len(seeds) / dt, res, dt
 
@@ -101,7 +101,7 @@ def reference_arm(args):
     try:
         for s in range(args.warmup + args.steps):
             seeds = [1000 * s + i for i in range(workers)]
-            v, _, dt = run_cpu_sample(pool, seeds, args.weights)
+            v, _, dt = run_cpu_sample(pool, seeds, args.weights, args.approximate_gradient)
             if s >= args.warmup:
                 times.append(dt)
     finally:
@@ -171,7 +171,8 @@ class ClockSampler:
 
 def workload_name(args):
     return (f"batch of independent synthetic 640x480 RGB-D pairs with known SE(3) motion (BASELINE.json configs[1] "
-            f"pair type, batched as configs[3]), {LEVELS}-level pyramid, weights={args.weights}")
+            f"pair type, batched as configs[3]), {LEVELS}-level pyramid, weights={args.weights}"
+            + (", approximate_image2_gradient" if getattr(args, "approximate_gradient", False) else ""))
 
 
 def measured_peak():
@@ -225,7 +226,7 @@ def gpu_arm(args):
 
     al = dvo.PairBatchAligner(cam, H, W, LEVELS, max_pairs=B, device=local_rank, weights=args.weights,
                               threads_per_block=args.threads, blocks_per_sm=args.blocks_per_sm,
-                              prefetch_rows=args.prefetch_rows)
+                              prefetch_rows=args.prefetch_rows, approximate_image2_gradient=args.approximate_gradient)
     from dense_visual_odometry_b200.sharding import gather_poses
 
     def step_resident():
@@ -314,8 +315,8 @@ def gpu_arm(args):
         workers = max(1, min(cores, n_cpu))
         pool = cpu_pool(workers)
         try:
-            run_cpu_sample(pool, [base + i for i in range(workers)], args.weights)       # warm the workers
-            v, res, dt = run_cpu_sample(pool, [base + i for i in range(n_cpu)], args.weights)
+            run_cpu_sample(pool, [base + i for i in range(workers)], args.weights, args.approximate_gradient)  # warm-up
+            v, res, dt = run_cpu_sample(pool, [base + i for i in range(n_cpu)], args.weights, args.approximate_gradient)
         finally:
             pool.close()
         dmax = max(float(np.abs(r[1] - qt_h[r[0] - base]).max()) for r in res)
@@ -372,6 +373,8 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--prefetch-rows", type=int, default=0)
+    ap.add_argument("--approximate-gradient", action="store_true",
+                    help="the reference's approximate_image2_gradient=True mode (not the headline configuration)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

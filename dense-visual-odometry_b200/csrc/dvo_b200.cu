@@ -86,16 +86,22 @@ extern "C" const char* dvo_last_error(const dvo_handle* h) { return h ? h->err.c
 typedef void (*align_fn)(const AlignParams);
 
 template <int T, int B>
-static align_fn pick_align(int w, int oob) {
-#define DVO_PICK(WM, OM) \
-    if (w == WM && oob == OM) return (align_fn)align_kernel<WM, OM, T, B>;
-    DVO_PICK(DVO_W_NONE, DVO_OOB_INCLUSIVE)
+static align_fn pick_align(int w, int oob, int grad) {
+#define DVO_PICK(WM, OM, GM) \
+    if (w == WM && oob == OM && grad == GM) return (align_fn)align_kernel<WM, OM, GM, T, B>;
+    DVO_PICK(DVO_W_NONE, DVO_OOB_INCLUSIVE, 0)
 #ifndef DVO_FAST_BUILD
-    DVO_PICK(DVO_W_NONE, DVO_OOB_STRICT)
-    DVO_PICK(DVO_W_TDIST_REF, DVO_OOB_INCLUSIVE)
-    DVO_PICK(DVO_W_TDIST_REF, DVO_OOB_STRICT)
-    DVO_PICK(DVO_W_HUBER, DVO_OOB_INCLUSIVE)
-    DVO_PICK(DVO_W_HUBER, DVO_OOB_STRICT)
+    DVO_PICK(DVO_W_NONE, DVO_OOB_STRICT, 0)
+    DVO_PICK(DVO_W_TDIST_REF, DVO_OOB_INCLUSIVE, 0)
+    DVO_PICK(DVO_W_TDIST_REF, DVO_OOB_STRICT, 0)
+    DVO_PICK(DVO_W_HUBER, DVO_OOB_INCLUSIVE, 0)
+    DVO_PICK(DVO_W_HUBER, DVO_OOB_STRICT, 0)
+    DVO_PICK(DVO_W_NONE, DVO_OOB_INCLUSIVE, 1)
+    DVO_PICK(DVO_W_NONE, DVO_OOB_STRICT, 1)
+    DVO_PICK(DVO_W_TDIST_REF, DVO_OOB_INCLUSIVE, 1)
+    DVO_PICK(DVO_W_TDIST_REF, DVO_OOB_STRICT, 1)
+    DVO_PICK(DVO_W_HUBER, DVO_OOB_INCLUSIVE, 1)
+    DVO_PICK(DVO_W_HUBER, DVO_OOB_STRICT, 1)
 #endif
 #undef DVO_PICK
     return nullptr;
@@ -105,20 +111,25 @@ static align_fn pick_align(int w, int oob) {
 // or 256 threads x 1 CTA per SM (lower latency for a single pair).  Both run 8 warps per SM at 255 registers;
 // shapes with more warps per SM spill inside the pipelined loop and measured slower (profiles/r1/SUMMARY.md).
 static align_fn get_align(const dvo_handle* h) {
-    const int w = h->cfg.weights, o = h->cfg.oob_mode;
-    if (h->threads == 256) return pick_align<256, 1>(w, o);
-    return pick_align<128, 2>(w, o);
+    const int w = h->cfg.weights, o = h->cfg.oob_mode, gm = h->cfg.approximate_image2_gradient ? 1 : 0;
+    if (h->threads == 256) return pick_align<256, 1>(w, o, gm);
+    return pick_align<128, 2>(w, o, gm);
 }
 
 typedef void (*dump_fn)(const AlignParams, int, int, int, const float*, float, float*, float*, uint8_t*, uint8_t*,
                         double*);
 static dump_fn get_dump(const dvo_handle* h) {
-    const int w = (h->cfg.weights == DVO_W_HUBER) ? DVO_W_HUBER : DVO_W_NONE;  // dump is unweighted unless Huber
-    if (w == DVO_W_HUBER)
-        return h->cfg.oob_mode == DVO_OOB_STRICT ? (dump_fn)dump_kernel<DVO_W_HUBER, DVO_OOB_STRICT>
-                                                 : (dump_fn)dump_kernel<DVO_W_HUBER, DVO_OOB_INCLUSIVE>;
-    return h->cfg.oob_mode == DVO_OOB_STRICT ? (dump_fn)dump_kernel<DVO_W_NONE, DVO_OOB_STRICT>
-                                             : (dump_fn)dump_kernel<DVO_W_NONE, DVO_OOB_INCLUSIVE>;
+    const bool hub = h->cfg.weights == DVO_W_HUBER;  // dump is unweighted unless Huber
+    const bool strict = h->cfg.oob_mode == DVO_OOB_STRICT;
+    const bool ap = h->cfg.approximate_image2_gradient != 0;
+#define DVO_DUMP(WM, OM, GM) (dump_fn) dump_kernel<WM, OM, GM>
+    if (ap) {
+        if (hub) return strict ? DVO_DUMP(DVO_W_HUBER, DVO_OOB_STRICT, 1) : DVO_DUMP(DVO_W_HUBER, DVO_OOB_INCLUSIVE, 1);
+        return strict ? DVO_DUMP(DVO_W_NONE, DVO_OOB_STRICT, 1) : DVO_DUMP(DVO_W_NONE, DVO_OOB_INCLUSIVE, 1);
+    }
+    if (hub) return strict ? DVO_DUMP(DVO_W_HUBER, DVO_OOB_STRICT, 0) : DVO_DUMP(DVO_W_HUBER, DVO_OOB_INCLUSIVE, 0);
+    return strict ? DVO_DUMP(DVO_W_NONE, DVO_OOB_STRICT, 0) : DVO_DUMP(DVO_W_NONE, DVO_OOB_INCLUSIVE, 0);
+#undef DVO_DUMP
 }
 
 __global__ void pose_matrix_kernel(const float* qt, float* T12) {
@@ -200,7 +211,7 @@ static int create_impl(dvo_handle* h) {
     }
     align_fn fn = get_align(h);
     if (!fn) {
-        h->err = "unsupported weights / oob_mode";
+        h->err = "unsupported weights / oob_mode / approximate_image2_gradient combination";
         return DVO_ERR_INVALID;
     }
     int occ = 0;
@@ -441,8 +452,8 @@ static void fill_params(const dvo_handle* h, AlignParams& p) {
     p.queue = h->queue;
     p.scratch = h->scratch;
     p.scratch_stride = h->scratch_stride;
-    // tuning knob (dvo_config.reserved[2]): L1 prefetch distance in rows; 0 = default (2), < 0 = off
-    p.prefetch_rows = h->cfg.reserved[2] > 0 ? h->cfg.reserved[2] : (h->cfg.reserved[2] < 0 ? 0 : 2);
+    // tuning knob (dvo_config.reserved[1]): L1 prefetch distance in rows; 0 = default (2), < 0 = off
+    p.prefetch_rows = h->cfg.reserved[1] > 0 ? h->cfg.reserved[1] : (h->cfg.reserved[1] < 0 ? 0 : 2);
 }
 
 extern "C" int dvo_estimate(dvo_handle* h, int prev_base, int cur_base, int n_pairs, const float* init_qt_dev,

@@ -93,7 +93,7 @@ class _Handle:
 
 def make_config(use_weighter=False, max_increased_steps_allowed=0, sigma=None, tolerance=1e-6, max_iterations=100,
                 weights: Optional[str] = None, oob_mode="inclusive", huber_k=None, max_distance=5.0,
-                threads_per_block=0, blocks_per_sm=0, prefetch_rows=0):
+                threads_per_block=0, blocks_per_sm=0, prefetch_rows=0, approximate_image2_gradient=False):
     lib = _cabi.load()
     cfg = _cabi.dvo_config()
     lib.dvo_default_config(C.byref(cfg))
@@ -114,7 +114,8 @@ def make_config(use_weighter=False, max_increased_steps_allowed=0, sigma=None, t
     cfg.max_distance = float(max_distance)
     cfg.threads_per_block = int(threads_per_block)
     cfg.blocks_per_sm = int(blocks_per_sm)
-    cfg.reserved[2] = int(prefetch_rows)  # tuning knob: L1 prefetch distance in rows (0 = default, < 0 = off, <= 32)
+    cfg.approximate_image2_gradient = 1 if approximate_image2_gradient else 0
+    cfg.reserved[1] = int(prefetch_rows)  # tuning knob: L1 prefetch distance in rows (0 = default, < 0 = off, <= 32)
     return cfg
 
 
@@ -140,8 +141,6 @@ class RobustDVOB200:
                  max_iterations: int = 100, approximate_image2_gradient: bool = False, height: int = None,
                  width: int = None, weights: Optional[str] = None, oob_mode: str = "inclusive",
                  huber_k: float = None, max_distance: float = 5.0, device: int = 0):
-        if approximate_image2_gradient:
-            raise NotImplementedError("approximate_image2_gradient=True is not built yet (SURVEY §8f item 4)")
         if levels < 1 or levels > _cabi.DVO_MAX_LEVELS:
             raise ValueError(f"levels must be in [1, {_cabi.DVO_MAX_LEVELS}], got {levels}")
         self._camera_model = camera_model
@@ -155,7 +154,9 @@ class RobustDVOB200:
         self._device = device
         # one pair at a time: a 256-thread CTA (8 warps on the pair) halves the latency of the 128-thread default
         self._cfg = make_config(use_weighter, max_increased_steps_allowed, sigma, tolerance, max_iterations, weights,
-                                oob_mode, huber_k, max_distance, threads_per_block=256)
+                                oob_mode, huber_k, max_distance, threads_per_block=256,
+                                approximate_image2_gradient=approximate_image2_gradient)
+        self._approx = bool(approximate_image2_gradient)
         self._h: Optional[_Handle] = None
         self._have_prev = False
         self._prev_slot = 0           # step(): slot holding the previous frame
@@ -282,7 +283,8 @@ class RobustDVOB200:
         pg, pd = self._fetch_prev()
         pgt = torch.as_tensor(pg).to(self._dev)
         pdt = torch.as_tensor(pd).to(self._dev)
-        self._h.call("dvo_build_pyramids_gray", ps, C.c_void_p(pgt.data_ptr()), C.c_void_p(pdt.data_ptr()), 1, 0, st)
+        self._h.call("dvo_build_pyramids_gray", ps, C.c_void_p(pgt.data_ptr()), C.c_void_p(pdt.data_ptr()), 1,
+                     1 if self._approx else 0, st)
         self._h.call("dvo_build_pyramids_gray", cs, C.c_void_p(g.data_ptr()), C.c_void_p(d.data_ptr()), 1, 1, st)
         torch.cuda.current_stream(self._dev).synchronize()
         self._hook_ready = True
@@ -353,6 +355,7 @@ class PairBatchAligner:
         self.max_pairs = int(max_pairs)
         self.levels = int(levels)
         self._cfg = make_config(**cfg_kwargs)
+        self._prev_grad = 1 if cfg_kwargs.get("approximate_image2_gradient") else 0  # I1 records are read then
         self._h = _Handle(device, height, width, levels, 2 * self.max_pairs, self.max_pairs, self._cfg)
         fx, fy, cx, cy, scale = _intrinsics_of(camera_model)
         self._h.call("dvo_set_intrinsics", fx, fy, cx, cy, scale)
@@ -378,10 +381,10 @@ class PairBatchAligner:
         st = _stream_ptr(torch, self._dev)
         if isinstance(bgr_prev, np.ndarray) or not bgr_prev.is_cuda:
             bp, dp, bc, dc = self._as_host_tensors(bgr_prev, depth_prev, bgr_cur, depth_cur)
-            self._h.call("dvo_build_pyramids_host", 0, self._ptr(bp), self._ptr(dp), B, 0, st)
+            self._h.call("dvo_build_pyramids_host", 0, self._ptr(bp), self._ptr(dp), B, self._prev_grad, st)
             self._h.call("dvo_build_pyramids_host", self.max_pairs, self._ptr(bc), self._ptr(dc), B, 1, st)
         else:
-            self._h.call("dvo_build_pyramids", 0, self._ptr(bgr_prev), self._ptr(depth_prev), B, 0, st)
+            self._h.call("dvo_build_pyramids", 0, self._ptr(bgr_prev), self._ptr(depth_prev), B, self._prev_grad, st)
             self._h.call("dvo_build_pyramids", self.max_pairs, self._ptr(bgr_cur), self._ptr(depth_cur), B, 1, st)
         self._B = B
 
@@ -437,7 +440,7 @@ class PairBatchAligner:
             n = min(chunk_pairs, B - lo)
             s = self._streams[k % 3]
             sp = C.c_void_p(s.cuda_stream)
-            self._h.call("dvo_build_pyramids_host", lo, self._ptr(bp[lo]), self._ptr(dp[lo]), n, 0, sp)
+            self._h.call("dvo_build_pyramids_host", lo, self._ptr(bp[lo]), self._ptr(dp[lo]), n, self._prev_grad, sp)
             self._h.call("dvo_build_pyramids_host", self.max_pairs + lo, self._ptr(bc[lo]), self._ptr(dc[lo]), n, 1, sp)
             init_ptr = self._ptr(init_dev[lo]) if init_dev is not None else None
             self._h.call("dvo_estimate", lo, self.max_pairs + lo, n, init_ptr, None, self._ptr(self._qt[lo]),

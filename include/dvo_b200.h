@@ -72,7 +72,10 @@ typedef struct dvo_config {
     float max_distance;          /* depth clamp in metres, default 5 */
     int32_t threads_per_block;   /* 0 = library default */
     int32_t blocks_per_sm;       /* 0 = library default */
-    int32_t reserved[4];
+    int32_t approximate_image2_gradient; /* base_robust_dvo.py:34-83 kwarg (cpu_...py:60-77): image Jacobian from the
+                                          * PREVIOUS frame's Sobel gradients at the unwarped pixel; frames used as
+                                          * "previous" must then be built with_gradients != 0. default 0 */
+    int32_t reserved[3];         /* reserved[1]: L1 prefetch distance in rows (0 default, < 0 off) */
 } dvo_config;
 
 /* Per-pair statistics written by dvo_estimate (index = pyramid level). 128 bytes. */

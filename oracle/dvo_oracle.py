@@ -430,16 +430,25 @@ class LevelData:
     mask: np.ndarray = None
     Jw: np.ndarray = None
     i1: np.ndarray = None
+    J_approx: np.ndarray = None  # approximate_image2_gradient: Jacobian fixed per level, from I1's gradients
 
 
-def prepare_level(K, depth_scale, gray_prev, depth_prev, gray_cur, level) -> LevelData:
-    """_setup (cpu_...py:54-58) + the pose-independent part of compute_residuals_and_jacobian."""
+def prepare_level(K, depth_scale, gray_prev, depth_prev, gray_cur, level, approximate: bool = False) -> LevelData:
+    """_setup (cpu_...py:54-77) + the pose-independent part of compute_residuals_and_jacobian.
+
+    approximate=True is the reference's `approximate_image2_gradient` mode (cpu_...py:60-77, :160-165): the image
+    Jacobian uses the Sobel gradients of the PREVIOUS image at the unwarped pixel, J = [I1x(x) I1y(x)] J_w, computed
+    once per level."""
     K_l = intrinsics_at(K, level)
-    gx, gy = sobel3(gray_cur)
+    gx, gy = sobel3(gray_prev if approximate else gray_cur)
     ld = LevelData(K_l, gray_prev, depth_prev, gray_cur, gx, gy)
     ld.P, ld.mask = deproject(depth_prev, K_l, depth_scale)
     ld.Jw = warp_jacobian(ld.P, K_l)
     ld.i1 = gray_prev[ld.mask]
+    if approximate:
+        g1x = gx[ld.mask].astype(F32)
+        g1y = gy[ld.mask].astype(F32)
+        ld.J_approx = (g1x[:, None] * ld.Jw[:, 0, :] + g1y[:, None] * ld.Jw[:, 1, :]).astype(F32)
     return ld
 
 
@@ -454,11 +463,14 @@ def residuals_and_jacobian(ld: LevelData, T: np.ndarray, oob_mode: int = OOB_INC
     xy = np.ascontiguousarray(uv[:2].T)
     i2 = interp_bilinear(ld.gray_cur, xy, oob_mode)
     valid = ~np.isnan(i2)
-    xyv = xy[valid]
-    gxv = interp_bilinear(ld.gx, xyv, oob_mode)
-    gyv = interp_bilinear(ld.gy, xyv, oob_mode)
-    Jw = ld.Jw[valid]
-    J = (gxv[:, None] * Jw[:, 0, :] + gyv[:, None] * Jw[:, 1, :]).astype(F32)
+    if ld.J_approx is not None:   # cpu_...py:187-188
+        J = ld.J_approx[valid]
+    else:
+        xyv = xy[valid]
+        gxv = interp_bilinear(ld.gx, xyv, oob_mode)
+        gyv = interp_bilinear(ld.gy, xyv, oob_mode)
+        Jw = ld.Jw[valid]
+        J = (gxv[:, None] * Jw[:, 0, :] + gyv[:, None] * Jw[:, 1, :]).astype(F32)
     r = (i2[valid] - ld.i1[valid]).astype(F32)
     return r, J, ld.mask, valid
 
@@ -509,7 +521,8 @@ def estimate_pose(K, depth_scale, gray_prev_pyr, depth_prev_pyr, gray_cur_pyr, l
                   weights: int = W_NONE, tolerance: float = 1e-6, max_iterations: int = 100,
                   max_increased_steps_allowed: int = 0, sigma: Optional[float] = None,
                   last_transform: Optional[Pose] = None, oob_mode: int = OOB_INCLUSIVE,
-                  huber_k: float = 1.345 * 5.0, tdist_kw: Optional[dict] = None) -> EstimateResult:
+                  huber_k: float = 1.345 * 5.0, tdist_kw: Optional[dict] = None,
+                  approximate_image2_gradient: bool = False) -> EstimateResult:
     """BaseRobustDVO._step (base_robust_dvo.py:137-236): coarse-to-fine Gauss-Newton."""
     est = (init or Pose()).copy()
     iters = [0] * levels
@@ -520,7 +533,8 @@ def estimate_pose(K, depth_scale, gray_prev_pyr, depth_prev_pyr, gray_cur_pyr, l
         old = (last_transform or Pose()).copy()
         err_prev = np.finfo("float32").max
         inc_count = 0
-        ld = prepare_level(K, depth_scale, gray_prev_pyr[level], depth_prev_pyr[level], gray_cur_pyr[level], level)
+        ld = prepare_level(K, depth_scale, gray_prev_pyr[level], depth_prev_pyr[level], gray_cur_pyr[level], level,
+                           approximate_image2_gradient)
         for i in range(max_iterations):
             r, J, _, valid = residuals_and_jacobian(ld, est.matrix(), oob_mode)
             H, b, err = normal_equations(r, J, weights, huber_k, tdist_kw)
@@ -556,7 +570,8 @@ class OracleDVO:
 
     def __init__(self, K, depth_scale, levels, initial_pose: Optional[Pose] = None, use_weighter=False,
                  max_increased_steps_allowed=0, sigma=None, tolerance=1e-6, max_iterations=100,
-                 max_distance=5.0, oob_mode=OOB_INCLUSIVE, weights: Optional[int] = None, huber_k=1.345 * 5.0):
+                 max_distance=5.0, oob_mode=OOB_INCLUSIVE, weights: Optional[int] = None, huber_k=1.345 * 5.0,
+                 approximate_image2_gradient=False):
         self.K = np.asarray(K, dtype=F32)[:3, :3]
         self.depth_scale = depth_scale
         self.levels = levels
@@ -564,7 +579,7 @@ class OracleDVO:
         self.weights = weights if weights is not None else (W_TDIST_REF if use_weighter else W_NONE)
         self.kw = dict(tolerance=tolerance, max_iterations=max_iterations,
                        max_increased_steps_allowed=max_increased_steps_allowed, sigma=sigma, oob_mode=oob_mode,
-                       huber_k=huber_k)
+                       huber_k=huber_k, approximate_image2_gradient=approximate_image2_gradient)
         self.max_distance = max_distance
         self._gray_prev = None
         self._depth_prev = None

@@ -460,3 +460,59 @@ def test_high_resolution_five_levels(dvo_mod, hw):
         ld = O.prepare_level(Km, d["depth_scale"], pg[lv], pd[lv], cg[lv], lv)
         _compare_level(est, m, ld, m.Se3.identity(), lv, O.OOB_INCLUSIVE, report)
     print("high-res dense parity:", hw, report)
+
+
+# ------------------------------------------------------------------------------------------------ approximate mode
+def test_approximate_gradient_dense_and_pose_vs_reference(dvo_mod, testdata_frames, golden_dir):
+    """`approximate_image2_gradient=True` (cpu_...py:60-77, :160-165, :187-188): J from the previous frame's Sobel
+    gradients at the unwarped pixel.  Per-pixel r / J / fused sums against the oracle, first-iteration J against the
+    REAL reference's vectors, full pose against the reference (the mode's flat error curve makes the stopping
+    iteration float-noise dependent, so iteration counts may differ by a few; the pose tolerance is the path's)."""
+    m = dvo_mod
+    f = testdata_frames
+    Km = _Km(f["K"])
+    est = _estimator(m, f["K"], f["depth_scale"], 4, approximate_image2_gradient=True)
+    est.step(f["bgr"][0], f["depth"][0].copy())
+    T = est.step(f["bgr"][1], f["depth"][1].copy())
+    g = np.load(golden_dir / "pose_testdata_1_2_approx.npz")
+    assert _check_pose(T, g) < POSE_TOL
+    print("approx iters", est.last_stats["iters"][0][:4].tolist(), g["iters"].tolist())
+    assert np.abs(est.last_stats["iters"][0][:4] - g["iters"]).max() <= 8
+    # dense parity of the mode's Jacobian
+    est = _estimator(m, f["K"], f["depth_scale"], 4, approximate_image2_gradient=True)
+    est.step(f["bgr"][0], f["depth"][0].copy())
+    est._build_pyramids(O.bgr_to_gray(f["bgr"][1]), O.clamp_depth(f["depth"][1], f["depth_scale"]))
+    gp0 = O.build_pyramid(O.bgr_to_gray(f["bgr"][0]), 4)
+    dp0 = O.build_pyramid(O.clamp_depth(f["depth"][0], f["depth_scale"]), 4)
+    gp1 = O.build_pyramid(O.bgr_to_gray(f["bgr"][1]), 4)
+    pose = m.Se3.from_se3(np.array([[0.0017], [-0.0072], [-0.0108], [0.005], [0.0065], [0.0034]], np.float32))
+    report = {}
+    for lv in range(4):
+        ld = O.prepare_level(Km, f["depth_scale"], gp0[lv], dp0[lv], gp1[lv], lv, approximate=True)
+        _compare_level(est, m, ld, pose, lv, O.OOB_INCLUSIVE, report)
+        # the reference's own first-iteration Jacobian rows (identity pose at the coarsest level)
+        if lv == 3:
+            r, J, mask, valid, acc = est.residuals_dense(m.Se3.identity(), lv, est._hook_slots[0], est._hook_slots[1])
+            Jv = J[valid][g[f"L{lv}_idx"]]
+            np.testing.assert_allclose(Jv, g[f"L{lv}_J"], rtol=1e-5, atol=1e-5 * np.abs(g[f"L{lv}_J"]).max())
+    print("approximate dense parity:", report)
+
+
+def test_approximate_gradient_batch_and_tdist(dvo_mod, testdata_frames, golden_dir):
+    m = dvo_mod
+    s = np.load(golden_dir / "pose_syn160.npz")
+    ga = np.load(golden_dir / "pose_syn160_approx.npz")
+    K = tuple(float(v) for v in s["K"])
+    cam = m.RGBDCameraModel(_Km(K), float(s["depth_scale"]))
+    rep = lambda a: np.ascontiguousarray(np.repeat(a[..., None], 3, axis=-1))  # noqa: E731
+    al = m.PairBatchAligner(cam, 120, 160, 3, max_pairs=3, approximate_image2_gradient=True)
+    qt, stats = al.align(rep(s["gray_prev"]), s["depth_prev"].copy(), rep(s["gray_cur"]), s["depth_cur"].copy())
+    for j in range(3):
+        assert np.abs(qt[j, :4] - ga[f"p{j}_q"]).max() < POSE_TOL
+        assert np.abs(qt[j, 4:] - ga[f"p{j}_t"]).max() < POSE_TOL
+    f = testdata_frames
+    g = np.load(golden_dir / "pose_testdata_1_2_approx_tdist.npz")
+    est = _estimator(m, f["K"], f["depth_scale"], 4, approximate_image2_gradient=True, use_weighter=True)
+    est.step(f["bgr"][0], f["depth"][0].copy())
+    T = est.step(f["bgr"][1], f["depth"][1].copy())
+    assert _check_pose(T, g) < POSE_TOL

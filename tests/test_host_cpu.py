@@ -99,8 +99,8 @@ def test_factory_errors_without_gpu(built):
         m.get_dvo("loftr", cam, m.Se3.identity(), levels=1)
     with pytest.raises(ValueError):
         m.get_dvo("robust-dvo", cam, m.Se3.identity(), levels=1, use_gpu=False)
-    with pytest.raises(ValueError):   # wrapped NotImplementedError, like the reference wraps ctor errors
-        m.get_dvo("robust-dvo", cam, m.Se3.identity(), levels=1, approximate_image2_gradient=True)
+    with pytest.raises(ValueError):   # constructor errors are wrapped like the reference wraps them
+        m.get_dvo("robust-dvo", cam, m.Se3.identity(), levels=99)
 
 
 def test_product_does_not_import_oracle():
