@@ -12,8 +12,9 @@ from .lie import Se3, So3, pose_to_qt
 from .estimator import (PairBatchAligner, RobustDVOB200, SequenceAligner, get_dvo, make_config, robust_dvo_factory,
                         stats_to_numpy)
 from ._cabi import DvoError
+from . import dataset
 from .sharding import chain_poses, gather_poses, sequence_shard_range, shard_range
 
 __all__ = ["RGBDCameraModel", "Se3", "So3", "pose_to_qt", "PairBatchAligner", "RobustDVOB200", "SequenceAligner", "get_dvo",
            "make_config", "robust_dvo_factory", "stats_to_numpy", "DvoError", "chain_poses", "gather_poses",
-           "sequence_shard_range", "shard_range"]
+           "sequence_shard_range", "shard_range", "dataset"]

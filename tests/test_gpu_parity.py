@@ -516,3 +516,26 @@ def test_approximate_gradient_batch_and_tdist(dvo_mod, testdata_frames, golden_d
     est.step(f["bgr"][0], f["depth"][0].copy())
     T = est.step(f["bgr"][1], f["depth"][1].copy())
     assert _check_pose(T, g) < POSE_TOL
+
+
+# ------------------------------------------------------------------------------------------------ sequence harness
+def test_run_sequence_batch_equals_streaming(dvo_mod, testdata_frames):
+    """dataset.run_sequence (the reference runner's loop, src/test_dvo.py:305-324): the batch route
+    (SequenceAligner) and the streaming route (step per frame) give the same trajectory and the report fields of
+    the reference; errors are distances to the ground-truth positions."""
+    from dense_visual_odometry_b200 import dataset as D
+    m = dvo_mod
+    f = testdata_frames
+    cam = m.RGBDCameraModel(_Km(f["K"]), f["depth_scale"])
+    gt_qt = np.stack([m.pose_to_qt(m.Se3(m.So3(np.asarray(T[:3, :3], dtype=np.float64)),
+                                         np.asarray(T[:3, 3], dtype=np.float32).reshape(3, 1))) for T in f["gt"][:6]])
+    init = m.Se3.from_qt(gt_qt[0])
+    a = D.run_sequence(f["bgr"][:6], np.stack([d.copy() for d in f["depth"][:6]]), cam, 4, initial_pose=init,
+                       batch=True, gt_qt=gt_qt)
+    b = D.run_sequence(f["bgr"][:6], np.stack([d.copy() for d in f["depth"][:6]]), cam, 4, initial_pose=init,
+                       batch=False, gt_qt=gt_qt)
+    assert len(a["trajectory"]) == 6 and len(a["estimated_transforms"]) == 6 and len(a["errors"]) == 6
+    np.testing.assert_allclose(np.array(a["estimated_poses"]), np.array(b["estimated_poses"]), atol=2e-5)
+    assert a["errors"][0] < 1e-6 and max(a["errors"]) < 0.05     # a few centimetres of drift over five frames
+    xyz = np.stack([p.tvec.reshape(3) for p in a["trajectory"]])
+    assert D.ate_rmse(xyz, gt_qt[:, 4:]) < 0.02
