@@ -65,10 +65,22 @@ __device__ inline void quat_log(const float* q, float* phi) {
 
 // Se3.exp as a 3x4 row-major matrix [R|t]; R = I when the rotation vector is shorter than 1e-6.
 __device__ inline void pose_matrix(const PoseQT& p, float* T) {
-    float phi[3];
-    quat_log(p.q, phi);
     float R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-    if (norm3f(phi) >= kLieEps) quat_to_R(p.q, R);
+    // Se3.exp uses R = I iff |So3.log| < 1e-6.  |log| = |wrap(2 atan2(n, w))| with n = |q_v|: for 0.5 < w < 1.5 and
+    // n >= 1e-6 that is at least 2 atan(n / 1.5) > 1.3e-6, and for n < 1e-6 the log is defined as 0 -- so the
+    // float64 atan2 is only needed for quaternions far from unit length or in the hemisphere w < 0.
+    const float n = norm3f(p.q + 1);
+    bool rotate;
+    if (n < kLieEps) {
+        rotate = false;
+    } else if (p.q[0] > 0.5f && p.q[0] < 1.5f) {
+        rotate = true;
+    } else {
+        float phi[3];
+        quat_log(p.q, phi);
+        rotate = norm3f(phi) >= kLieEps;
+    }
+    if (rotate) quat_to_R(p.q, R);
     T[0] = R[0]; T[1] = R[1]; T[2] = R[2];  T[3] = p.t[0];
     T[4] = R[3]; T[5] = R[4]; T[6] = R[5];  T[7] = p.t[1];
     T[8] = R[6]; T[9] = R[7]; T[10] = R[8]; T[11] = p.t[2];
@@ -220,49 +232,47 @@ __device__ inline void pose_log(const PoseQT& p, float* xi) {
 // safely positive relative to the largest diagonal entry drops that unknown (x_i = 0), which is what
 // the reference's minimum-norm gelsy solve (base_robust_dvo.py:196-198, rcond = eps(float32)) does
 // for an exactly decoupled degenerate direction.  Returns the number of dropped unknowns.
-__device__ inline int solve6_ldlt(const double* Hin, const double* b, double* x) {
-    double L[36];
-    double d[6];
-    bool drop[6];
+// Fully unrolled (everything stays in registers): a dropped pivot gets d = 1/d = 0, which zeroes its
+// column of L and its unknown without any further branching.
+__device__ __forceinline__ int solve6_ldlt(const double* Hin, const double* b, double* x) {
+    double L[6][6];
+    double d[6], dinv[6];
     double dmax = 0.0;
 #pragma unroll
     for (int i = 0; i < 6; ++i) dmax = fmax(dmax, fabs(Hin[i * 6 + i]));
     const double tiny = dmax * 1.1920929e-07;
     int ndrop = 0;
+#pragma unroll
     for (int j = 0; j < 6; ++j) {
         double dj = Hin[j * 6 + j];
-        for (int k = 0; k < j; ++k)
-            if (!drop[k]) dj -= L[j * 6 + k] * L[j * 6 + k] * d[k];
-        drop[j] = !(dj > tiny);
-        if (drop[j]) {
-            ++ndrop;
-            d[j] = 0.0;
-            for (int i = j + 1; i < 6; ++i) L[i * 6 + j] = 0.0;
-            continue;
-        }
-        d[j] = dj;
-        const double inv = 1.0 / dj;
+#pragma unroll
+        for (int k = 0; k < j; ++k) dj -= L[j][k] * L[j][k] * d[k];
+        const bool ok = dj > tiny;
+        ndrop += ok ? 0 : 1;
+        d[j] = ok ? dj : 0.0;
+        dinv[j] = ok ? 1.0 / dj : 0.0;
+#pragma unroll
         for (int i = j + 1; i < 6; ++i) {
-            double s = Hin[i * 6 + j];
-            for (int k = 0; k < j; ++k)
-                if (!drop[k]) s -= L[i * 6 + k] * L[j * 6 + k] * d[k];
-            L[i * 6 + j] = s * inv;
+            double sum = Hin[i * 6 + j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) sum -= L[i][k] * L[j][k] * d[k];
+            L[i][j] = sum * dinv[j];
         }
     }
     double y[6];
+#pragma unroll
     for (int i = 0; i < 6; ++i) {
-        double s = b[i];
-        for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * y[k];
-        y[i] = drop[i] ? 0.0 : s;
+        double sum = b[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) sum -= L[i][k] * y[k];
+        y[i] = (dinv[i] != 0.0) ? sum : 0.0;
     }
+#pragma unroll
     for (int i = 5; i >= 0; --i) {
-        if (drop[i]) {
-            x[i] = 0.0;
-            continue;
-        }
-        double s = y[i] / d[i];
-        for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * x[k];
-        x[i] = s;
+        double sum = y[i] * dinv[i];
+#pragma unroll
+        for (int k = i + 1; k < 6; ++k) sum -= L[k][i] * x[k];
+        x[i] = sum;
     }
     return ndrop;
 }

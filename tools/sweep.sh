@@ -1,4 +1,5 @@
-for cfg in "--threads 128" "--threads 160" "--threads 256"; do
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+for cfg in "--threads 128" "--threads 128 --approximate-gradient" "--threads 256"; do
 python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1 --pairs 2048 $cfg 2>&1 | tail -1 | python -c "
 import sys,json
 for l in sys.stdin:
