@@ -116,6 +116,25 @@ static align_fn get_align(const dvo_handle* h) {
     return pick_align<128, 2>(w, o, gm);
 }
 
+// Cluster-mode kernel (one thread-block cluster per pair); not built for the t-distribution weights.
+static align_fn get_cluster(const dvo_handle* h) {
+    const int w = h->cfg.weights, o = h->cfg.oob_mode, gm = h->cfg.approximate_image2_gradient ? 1 : 0;
+#define DVO_PICKC(WM, OM, GM) \
+    if (w == WM && o == OM && gm == GM) return (align_fn)align_cluster_kernel<WM, OM, GM>;
+    DVO_PICKC(DVO_W_NONE, DVO_OOB_INCLUSIVE, 0)
+#ifndef DVO_FAST_BUILD
+    DVO_PICKC(DVO_W_NONE, DVO_OOB_STRICT, 0)
+    DVO_PICKC(DVO_W_HUBER, DVO_OOB_INCLUSIVE, 0)
+    DVO_PICKC(DVO_W_HUBER, DVO_OOB_STRICT, 0)
+    DVO_PICKC(DVO_W_NONE, DVO_OOB_INCLUSIVE, 1)
+    DVO_PICKC(DVO_W_NONE, DVO_OOB_STRICT, 1)
+    DVO_PICKC(DVO_W_HUBER, DVO_OOB_INCLUSIVE, 1)
+    DVO_PICKC(DVO_W_HUBER, DVO_OOB_STRICT, 1)
+#endif
+#undef DVO_PICKC
+    return nullptr;
+}
+
 typedef void (*dump_fn)(const AlignParams, int, int, int, const float*, float, float*, float*, uint8_t*, uint8_t*,
                         double*);
 static dump_fn get_dump(const dvo_handle* h) {
@@ -207,6 +226,11 @@ static int create_impl(dvo_handle* h) {
     h->threads = h->cfg.threads_per_block ? h->cfg.threads_per_block : 128;
     if (h->threads != 128 && h->threads != 256) {
         h->err = "threads_per_block must be 0, 128 or 256";
+        return DVO_ERR_INVALID;
+    }
+    if (h->cfg.cluster_size != 0 && h->cfg.cluster_size != 1 && h->cfg.cluster_size != 2 && h->cfg.cluster_size != 4 &&
+        h->cfg.cluster_size != 8 && h->cfg.cluster_size != 16) {
+        h->err = "cluster_size must be 0, 1, 2, 4, 8 or 16";
         return DVO_ERR_INVALID;
     }
     align_fn fn = get_align(h);
@@ -452,8 +476,8 @@ static void fill_params(const dvo_handle* h, AlignParams& p) {
     p.queue = h->queue;
     p.scratch = h->scratch;
     p.scratch_stride = h->scratch_stride;
-    // tuning knob (dvo_config.reserved[1]): L1 prefetch distance in rows; 0 = default (2), < 0 = off
-    p.prefetch_rows = h->cfg.reserved[1] > 0 ? h->cfg.reserved[1] : (h->cfg.reserved[1] < 0 ? 0 : 2);
+    // tuning knob (dvo_config.reserved[0]): L1 prefetch distance in rows; 0 = default (2), < 0 = off
+    p.prefetch_rows = h->cfg.reserved[0] > 0 ? h->cfg.reserved[0] : (h->cfg.reserved[0] < 0 ? 0 : 2);
 }
 
 extern "C" int dvo_estimate(dvo_handle* h, int prev_base, int cur_base, int n_pairs, const float* init_qt_dev,
@@ -481,9 +505,28 @@ extern "C" int dvo_estimate(dvo_handle* h, int prev_base, int cur_base, int n_pa
     DVO_CUDA(h, cudaMemsetAsync(p.queue, 0, sizeof(int), st));
     const int grid = n_pairs < h->grid_max ? n_pairs : h->grid_max;
     align_fn fn = get_align(h);
+    align_fn cfn = (h->cfg.cluster_size > 1) ? get_cluster(h) : nullptr;
     DVO_CUDA(h, cudaEventRecord(h->ev0, st));
     void* args[] = {&p};
-    DVO_CUDA(h, cudaLaunchKernel((const void*)fn, dim3(grid), dim3(h->threads), args, 0, st));
+    if (cfn) {
+        const int C = h->cfg.cluster_size;
+        if (C > 8) DVO_CUDA(h, cudaFuncSetAttribute((const void*)cfn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3((unsigned)n_pairs * (unsigned)C);
+        lc.blockDim = dim3(128);
+        lc.dynamicSmemBytes = 0;
+        lc.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)C;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        lc.attrs = at;
+        lc.numAttrs = 1;
+        DVO_CUDA(h, cudaLaunchKernelExC(&lc, (const void*)cfn, args));
+    } else {
+        DVO_CUDA(h, cudaLaunchKernel((const void*)fn, dim3(grid), dim3(h->threads), args, 0, st));
+    }
     DVO_CUDA(h, cudaEventRecord(h->ev1, st));
     h->ev_valid = true;
     h->launches += 1;

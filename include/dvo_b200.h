@@ -75,7 +75,9 @@ typedef struct dvo_config {
     int32_t approximate_image2_gradient; /* base_robust_dvo.py:34-83 kwarg (cpu_...py:60-77): image Jacobian from the
                                           * PREVIOUS frame's Sobel gradients at the unwarped pixel; frames used as
                                           * "previous" must then be built with_gradients != 0. default 0 */
-    int32_t reserved[3];         /* reserved[1]: L1 prefetch distance in rows (0 default, < 0 off) */
+    int32_t cluster_size;        /* 0/1 = one CTA per pair (throughput); 2, 4, 8 or 16 = one thread-block cluster per
+                                  * pair (latency of single pairs and short batches); ignored with t-dist weights */
+    int32_t reserved[2];         /* reserved[0]: L1 prefetch distance in rows (0 default, < 0 off) */
 } dvo_config;
 
 /* Per-pair statistics written by dvo_estimate (index = pyramid level). 128 bytes. */

@@ -539,3 +539,55 @@ def test_run_sequence_batch_equals_streaming(dvo_mod, testdata_frames):
     assert a["errors"][0] < 1e-6 and max(a["errors"]) < 0.05     # a few centimetres of drift over five frames
     xyz = np.stack([p.tvec.reshape(3) for p in a["trajectory"]])
     assert D.ate_rmse(xyz, gt_qt[:, 4:]) < 0.02
+
+
+# ------------------------------------------------------------------------------------------------ cluster mode
+@pytest.mark.parametrize("cluster", [2, 8, 16])
+def test_cluster_mode_matches_reference_and_single_cta(dvo_mod, testdata_frames, golden_dir, cluster):
+    """One thread-block cluster per pair (partial sums combined through distributed shared memory): same pose as
+    the REAL reference and as the one-CTA kernel, deterministic from run to run."""
+    m = dvo_mod
+    f = testdata_frames
+    cam = m.RGBDCameraModel(_Km(f["K"]), f["depth_scale"])
+    rep = lambda k: (np.stack(f["bgr"][k:k + 2]), np.stack([d.copy() for d in f["depth"][k:k + 2]]))  # noqa: E731
+    g = np.load(golden_dir / "pose_testdata_1_2.npz")
+    single = m.SequenceAligner(cam, 480, 640, 4, max_frames=2)
+    clus = m.SequenceAligner(cam, 480, 640, 4, max_frames=2, cluster_size=cluster)
+    q0, s0 = single.align(*rep(0))
+    q1, s1 = clus.align(*rep(0))
+    q2, s2 = clus.align(*rep(0))
+    np.testing.assert_array_equal(q1, q2)                      # run-to-run deterministic
+    assert np.abs(q1 - q0).max() < 5e-6
+    assert np.abs(q1[0, :4] - g["q"].reshape(4)).max() < POSE_TOL and np.abs(q1[0, 4:] - g["t"].reshape(3)).max() < POSE_TOL
+    assert np.abs(s1["iters"][0][:4] - g["iters"]).max() <= 2
+    np.testing.assert_array_equal(s1["n_valid"][0][:4], s0["n_valid"][0][:4])
+
+
+def test_cluster_mode_odd_sizes_huber_and_approximate(dvo_mod, golden_dir):
+    m = dvo_mod
+    rep = lambda a: np.ascontiguousarray(np.repeat(a[..., None], 3, axis=-1))  # noqa: E731
+    for name in ("syn101", "syn160"):
+        g = np.load(golden_dir / f"pose_{name}.npz")
+        K = tuple(float(v) for v in g["K"])
+        B, h, w = g["gray_prev"].shape
+        cam = m.RGBDCameraModel(_Km(K), float(g["depth_scale"]))
+        al = m.PairBatchAligner(cam, h, w, int(g["levels"]), max_pairs=B, cluster_size=4)
+        qt, _ = al.align(rep(g["gray_prev"]), g["depth_prev"].copy(), rep(g["gray_cur"]), g["depth_cur"].copy())
+        for j in range(B):
+            assert np.abs(qt[j, :4] - g[f"p{j}_none_q"]).max() < POSE_TOL
+            assert np.abs(qt[j, 4:] - g[f"p{j}_none_t"]).max() < POSE_TOL
+        for kw in ({"weights": "huber"}, {"approximate_image2_gradient": True}):
+            a = m.PairBatchAligner(cam, h, w, int(g["levels"]), max_pairs=B, **kw)
+            b = m.PairBatchAligner(cam, h, w, int(g["levels"]), max_pairs=B, cluster_size=8, **kw)
+            args = (rep(g["gray_prev"]), g["depth_prev"].copy(), rep(g["gray_cur"]), g["depth_cur"].copy())
+            qa, _ = a.align(*args)
+            qb, _ = b.align(*args)
+            assert np.abs(qa - qb).max() < 2e-5, kw
+    # t-distribution weights ignore the cluster request and still match the reference
+    g = np.load(golden_dir / "pose_syn160.npz")
+    cam = m.RGBDCameraModel(_Km(tuple(float(v) for v in g["K"])), float(g["depth_scale"]))
+    al = m.PairBatchAligner(cam, 120, 160, 3, max_pairs=1, use_weighter=True, cluster_size=8)
+    qt, _ = al.align(rep(g["gray_prev"][:1]), g["depth_prev"][:1].copy(), rep(g["gray_cur"][:1]), g["depth_cur"][:1].copy())
+    assert np.abs(qt[0, :4] - g["p0_tdist_q"]).max() < POSE_TOL and np.abs(qt[0, 4:] - g["p0_tdist_t"]).max() < POSE_TOL
+    with pytest.raises(Exception):
+        m.PairBatchAligner(cam, 120, 160, 3, max_pairs=1, cluster_size=3)
