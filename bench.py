@@ -325,6 +325,24 @@ def gpu_arm(args):
                "sample": f"{n_cpu} of the timed pairs (seeds {base}..{base + n_cpu - 1}), one process per pair, BLAS 1 "
                          f"thread each, {dt:.1f} s wall; oracle/dvo_oracle.py (NumPy port pinned to the reference)"}
 
+    latency = None
+    if rank == 0:
+        # single-pair latency through the reference's own call, step(color, depth) with host arrays (cluster mode)
+        est = dvo.get_dvo("robust-dvo", cam, dvo.Se3.identity(), levels=LEVELS, weights=args.weights,
+                          approximate_image2_gradient=args.approximate_gradient)
+        f0 = (bp[0].cpu().numpy(), dp[0].cpu().numpy())
+        f1 = (bc[0].cpu().numpy(), dc[0].cpu().numpy())
+        lat, kms = [], []
+        for i in range(7):
+            est.step(f0[0], f0[1].copy())
+            t0 = time.perf_counter()
+            est.step(f1[0], f1[1].copy())
+            lat.append(1e3 * (time.perf_counter() - t0))
+            kms.append(est._h.last_estimate_ms())
+        latency = {"single_pair_step_ms": float(np.median(lat[2:])), "single_pair_kernel_ms": float(np.median(kms[2:])),
+                   "cluster_size": 8 if args.weights != "tdist" else 1,
+                   "note": "one 640x480 pair through get_dvo(...).step(color, depth): H2D of the frame, pyramids, "
+                           "estimate on one thread-block cluster, D2H of the pose"}
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -351,6 +369,7 @@ def gpu_arm(args):
                          "frac_within_1e-4": float(np.mean(np.array(pose_err) < 1e-4)),
                          "flags_nonzero": int((stats["flags"] != 0).sum())},
             "parity": parity,
+            "latency": latency,
         }
         print(json.dumps(out), flush=True)
     if world > 1:
