@@ -337,12 +337,12 @@ extern "C" long long dvo_launch_count(const dvo_handle* h) { return h ? h->launc
 // ---- pyramids ----------------------------------------------------------------------------------
 static int build_levels(dvo_handle* h, int frame_base, int n_frames, int with_gradients, cudaStream_t st) {
     for (int l = 1; l < h->levels; ++l) {
-        dim3 grid((h->lw[l] + 255) / 256, h->lh[l], n_frames);
-        median3_down_kernel<uint8_t><<<grid, 256, 0, st>>>(
+        dim3 grid(((h->lw[l] + 3) / 4 + 127) / 128, h->lh[l], n_frames);
+        median3_down_kernel<uint8_t><<<grid, 128, 0, st>>>(
             h->gray[l - 1] + (size_t)frame_base * h->lplane[l - 1], h->gray[l] + (size_t)frame_base * h->lplane[l],
             h->lw[l - 1], h->lh[l - 1], h->lpitch[l - 1], h->lplane[l - 1], h->lw[l], h->lh[l], h->lpitch[l],
             h->lplane[l]);
-        median3_down_kernel<uint16_t><<<grid, 256, 0, st>>>(
+        median3_down_kernel<uint16_t><<<grid, 128, 0, st>>>(
             h->depth[l - 1] + (size_t)frame_base * h->lplane[l - 1], h->depth[l] + (size_t)frame_base * h->lplane[l],
             h->lw[l - 1], h->lh[l - 1], h->lpitch[l - 1], h->lplane[l - 1], h->lw[l], h->lh[l], h->lpitch[l],
             h->lplane[l]);
@@ -350,8 +350,8 @@ static int build_levels(dvo_handle* h, int frame_base, int n_frames, int with_gr
     }
     if (with_gradients) {
         for (int l = 0; l < h->levels; ++l) {
-            dim3 grid((h->lw[l] + 255) / 256, h->lh[l], n_frames);
-            sobel3_kernel<<<grid, 256, 0, st>>>(h->gray[l] + (size_t)frame_base * h->lplane[l],
+            dim3 grid(((h->lw[l] + 3) / 4 + 127) / 128, h->lh[l], n_frames);
+            sobel3_kernel<<<grid, 128, 0, st>>>(h->gray[l] + (size_t)frame_base * h->lplane[l],
                                                 h->rec[l] + (size_t)frame_base * h->lplane[l], h->lw[l], h->lh[l],
                                                 h->lpitch[l], h->lplane[l]);
             h->launches += 1;
@@ -452,7 +452,8 @@ static void fill_params(const dvo_handle* h, AlignParams& p) {
         g.h_magic = (unsigned)((1ull << 32) / (unsigned)h->lh[l]) + 1u;
         {   // chunks per strip = NW * k with about 60 rows per chunk (align_kernel.cuh, fused_pass)
             const int nw = h->threads / 32;
-            int k = (h->lh[l] + nw * 30) / (nw * 60);
+            const int target = h->cfg.reserved[1] > 0 ? h->cfg.reserved[1] : 60;  // tuning knob: rows per chunk
+            int k = (h->lh[l] + nw * target / 2) / (nw * target);
             if (k < 1) k = 1;
             g.chunks_per_strip = nw * k;
             g.chunk_rows = (h->lh[l] + g.chunks_per_strip - 1) / g.chunks_per_strip;

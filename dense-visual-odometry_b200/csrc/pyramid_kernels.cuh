@@ -116,47 +116,101 @@ __device__ __forceinline__ T median9(T p0, T p1, T p2, T p3, T p4, T p5, T p6, T
     return p4;
 }
 
-// One thread per OUTPUT pixel: only the kept (even, even) medians are computed.
+// Nine source values of one row feeding FOUR consecutive outputs ox = 4k .. 4k+3: source columns
+// 8k-1 .. 8k+7, border replicated.  Interior threads use one scalar + one 8-element vector load (rows start
+// 16-byte aligned because every pitch is a multiple of 64); the first and the last thread of a row clamp.
 template <typename T>
-__global__ void __launch_bounds__(256) median3_down_kernel(const T* __restrict__ src, T* __restrict__ dst, int sw,
+__device__ __forceinline__ void load_row9(const T* __restrict__ row, int k, int sw, int* v) {
+    const int c0 = 8 * k;
+    if (k > 0 && c0 + 7 < sw) {
+        v[0] = (int)__ldg(row + c0 - 1);
+        if (sizeof(T) == 1) {
+            const uint2 w = __ldg(reinterpret_cast<const uint2*>(row + c0));
+            v[1] = w.x & 255u; v[2] = (w.x >> 8) & 255u; v[3] = (w.x >> 16) & 255u; v[4] = w.x >> 24;
+            v[5] = w.y & 255u; v[6] = (w.y >> 8) & 255u; v[7] = (w.y >> 16) & 255u; v[8] = w.y >> 24;
+        } else {
+            const uint4 w = __ldg(reinterpret_cast<const uint4*>(row + c0));
+            v[1] = w.x & 65535u; v[2] = w.x >> 16; v[3] = w.y & 65535u; v[4] = w.y >> 16;
+            v[5] = w.z & 65535u; v[6] = w.z >> 16; v[7] = w.w & 65535u; v[8] = w.w >> 16;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) v[j] = (int)__ldg(row + min(max(c0 - 1 + j, 0), sw - 1));
+    }
+}
+
+// One thread per FOUR output pixels of a row: only the kept (even, even) medians are computed.
+template <typename T>
+__global__ void __launch_bounds__(128) median3_down_kernel(const T* __restrict__ src, T* __restrict__ dst, int sw,
                                                            int sh, int spitch, size_t splane, int dw, int dh,
                                                            int dpitch, size_t dplane) {
-    const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int oy = blockIdx.y;
     const int frame = blockIdx.z;
+    const int ox = 4 * k;
     if (ox >= dw) return;
-    const int cx = ox * 2, cy = oy * 2;
-    const int x0 = max(cx - 1, 0), x2 = min(cx + 1, sw - 1);
-    const int y0 = max(cy - 1, 0), y2 = min(cy + 1, sh - 1);
+    const int cy = oy * 2;
     const T* s = src + (size_t)frame * splane;
-    const T* r0 = s + (size_t)y0 * spitch;
-    const T* r1 = s + (size_t)cy * spitch;
-    const T* r2 = s + (size_t)y2 * spitch;
-    using W = int;
-    const W m = median9<W>(__ldg(r0 + x0), __ldg(r0 + cx), __ldg(r0 + x2), __ldg(r1 + x0), __ldg(r1 + cx),
-                           __ldg(r1 + x2), __ldg(r2 + x0), __ldg(r2 + cx), __ldg(r2 + x2));
-    dst[(size_t)frame * dplane + (size_t)oy * dpitch + ox] = (T)m;
+    int r0[9], r1[9], r2[9];
+    load_row9(s + (size_t)max(cy - 1, 0) * spitch, k, sw, r0);
+    load_row9(s + (size_t)cy * spitch, k, sw, r1);
+    load_row9(s + (size_t)min(cy + 1, sh - 1) * spitch, k, sw, r2);
+    int m[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        m[j] = median9<int>(r0[2 * j], r0[2 * j + 1], r0[2 * j + 2], r1[2 * j], r1[2 * j + 1], r1[2 * j + 2],
+                            r2[2 * j], r2[2 * j + 1], r2[2 * j + 2]);
+    T* d = dst + (size_t)frame * dplane + (size_t)oy * dpitch + ox;
+    if (ox + 3 < dw) {
+        if (sizeof(T) == 1)
+            *reinterpret_cast<uint32_t*>(d) = (uint32_t)m[0] | ((uint32_t)m[1] << 8) | ((uint32_t)m[2] << 16) | ((uint32_t)m[3] << 24);
+        else
+            *reinterpret_cast<uint2*>(d) = make_uint2((uint32_t)m[0] | ((uint32_t)m[1] << 16), (uint32_t)m[2] | ((uint32_t)m[3] << 16));
+    } else {
+        for (int j = 0; j < 4 && ox + j < dw; ++j) d[j] = (T)m[j];   // padding columns stay zero
+    }
 }
 
 // ---- a9 -----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sobel3_kernel(const uint8_t* __restrict__ gray, uint2* __restrict__ rec,
+// One thread per FOUR pixels of a row: columns 4k-1 .. 4k+4 of three rows (one 32-bit load + two bytes each),
+// four packed records out as two 16-byte stores.
+__device__ __forceinline__ void load_row6(const uint8_t* __restrict__ row, int x0, int w, int* v) {
+    v[0] = (int)__ldg(row + max(x0 - 1, 0));
+    if (x0 + 3 < w) {
+        const uint32_t q = __ldg(reinterpret_cast<const uint32_t*>(row + x0));
+        v[1] = q & 255u; v[2] = (q >> 8) & 255u; v[3] = (q >> 16) & 255u; v[4] = q >> 24;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[1 + j] = (int)__ldg(row + min(x0 + j, w - 1));
+    }
+    v[5] = (int)__ldg(row + min(x0 + 4, w - 1));
+}
+
+__global__ void __launch_bounds__(128) sobel3_kernel(const uint8_t* __restrict__ gray, uint2* __restrict__ rec,
                                                      int w, int h, int pitch, size_t plane) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
     const int y = blockIdx.y;
     const int frame = blockIdx.z;
-    if (x >= w) return;
-    const int xm = max(x - 1, 0), xp = min(x + 1, w - 1);
-    const int ym = max(y - 1, 0), yp = min(y + 1, h - 1);
+    if (x0 >= w) return;
     const uint8_t* s = gray + (size_t)frame * plane;
-    const uint8_t* r0 = s + (size_t)ym * pitch;
-    const uint8_t* r1 = s + (size_t)y * pitch;
-    const uint8_t* r2 = s + (size_t)yp * pitch;
-    const int a00 = __ldg(r0 + xm), a01 = __ldg(r0 + x), a02 = __ldg(r0 + xp);
-    const int a10 = __ldg(r1 + xm), a11 = __ldg(r1 + x), a12 = __ldg(r1 + xp);
-    const int a20 = __ldg(r2 + xm), a21 = __ldg(r2 + x), a22 = __ldg(r2 + xp);
-    const int gx = (a02 + 2 * a12 + a22) - (a00 + 2 * a10 + a20);
-    const int gy = (a20 + 2 * a21 + a22) - (a00 + 2 * a01 + a02);
-    rec[(size_t)frame * plane + (size_t)y * pitch + x] = rec_pack(gx, gy, a11);
+    int a[6], b[6], c[6];
+    load_row6(s + (size_t)max(y - 1, 0) * pitch, x0, w, a);
+    load_row6(s + (size_t)y * pitch, x0, w, b);
+    load_row6(s + (size_t)min(y + 1, h - 1) * pitch, x0, w, c);
+    uint2 out[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int gx = (a[j + 2] + 2 * b[j + 2] + c[j + 2]) - (a[j] + 2 * b[j] + c[j]);
+        const int gy = (c[j] + 2 * c[j + 1] + c[j + 2]) - (a[j] + 2 * a[j + 1] + a[j + 2]);
+        out[j] = rec_pack(gx, gy, b[j + 1]);
+    }
+    uint2* d = rec + (size_t)frame * plane + (size_t)y * pitch + x0;
+    if (x0 + 3 < w) {
+        reinterpret_cast<uint4*>(d)[0] = make_uint4(out[0].x, out[0].y, out[1].x, out[1].y);
+        reinterpret_cast<uint4*>(d)[1] = make_uint4(out[2].x, out[2].y, out[3].x, out[3].y);
+    } else {
+        for (int j = 0; j < 4 && x0 + j < w; ++j) d[j] = out[j];   // padding columns stay zero
+    }
 }
 
 // Dense read-back of one level plane (drops the pitch padding); used by dvo_get_pyramid.

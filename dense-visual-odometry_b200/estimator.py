@@ -95,7 +95,7 @@ class _Handle:
 def make_config(use_weighter=False, max_increased_steps_allowed=0, sigma=None, tolerance=1e-6, max_iterations=100,
                 weights: Optional[str] = None, oob_mode="inclusive", huber_k=None, max_distance=5.0,
                 threads_per_block=0, blocks_per_sm=0, prefetch_rows=0, approximate_image2_gradient=False,
-                cluster_size=0):
+                cluster_size=0, chunk_rows=0):
     lib = _cabi.load()
     cfg = _cabi.dvo_config()
     lib.dvo_default_config(C.byref(cfg))
@@ -118,6 +118,7 @@ def make_config(use_weighter=False, max_increased_steps_allowed=0, sigma=None, t
     cfg.blocks_per_sm = int(blocks_per_sm)
     cfg.approximate_image2_gradient = 1 if approximate_image2_gradient else 0
     cfg.cluster_size = int(cluster_size)
+    cfg.reserved[1] = int(chunk_rows)     # tuning knob: target rows per work chunk (0 = default 60)
     cfg.reserved[0] = int(prefetch_rows)  # tuning knob: L1 prefetch distance in rows (0 = default, < 0 = off, <= 32)
     return cfg
 
