@@ -591,3 +591,59 @@ def test_cluster_mode_odd_sizes_huber_and_approximate(dvo_mod, golden_dir):
     assert np.abs(qt[0, :4] - g["p0_tdist_q"]).max() < POSE_TOL and np.abs(qt[0, 4:] - g["p0_tdist_t"]).max() < POSE_TOL
     with pytest.raises(Exception):
         m.PairBatchAligner(cam, 120, 160, 3, max_pairs=1, cluster_size=3)
+
+
+# ------------------------------------------------------------------------------------------------ properties at full size
+def test_batch_position_independence_full_size(dvo_mod):
+    """Size-independent property at the benchmark's frame size: a pair's result does not depend on where it sits
+    in a batch, on the batch size, or on which CTA picks it up (bit-identical), and both launch shapes and the
+    cluster mode agree with it to float32 summation noise."""
+    import torch
+    from dense_visual_odometry_b200.synthetic import make_pairs_numpy, TUM_FR1, TUM_DEPTH_SCALE
+    m = dvo_mod
+    d = make_pairs_numpy([11, 12, 13], height=480, width=640)
+    cam = m.RGBDCameraModel(_Km(TUM_FR1), TUM_DEPTH_SCALE)
+    order = [0, 1, 2, 1, 0, 2, 2, 1, 0, 0, 1, 2] * 28          # 336 pairs: more than one wave of 296 CTA slots
+    pick = lambda k: np.ascontiguousarray(d[k][order])           # noqa: E731
+    al = m.PairBatchAligner(cam, 480, 640, 4, max_pairs=len(order))
+    qt, st = al.align(pick("bgr_prev"), pick("depth_prev"), pick("bgr_cur"), pick("depth_cur"))
+    for s in range(3):
+        rows = [i for i, o in enumerate(order) if o == s]
+        assert all(np.array_equal(qt[rows[0]], qt[r]) for r in rows)
+        assert all(np.array_equal(st["iters"][rows[0]], st["iters"][r]) for r in rows)
+    small = m.PairBatchAligner(cam, 480, 640, 4, max_pairs=3)
+    q3, _ = small.align(d["bgr_prev"], d["depth_prev"].copy(), d["bgr_cur"], d["depth_cur"].copy())
+    np.testing.assert_array_equal(q3, qt[:3])
+    for kw in ({"threads_per_block": 256}, {"cluster_size": 8}):
+        other = m.PairBatchAligner(cam, 480, 640, 4, max_pairs=3, **kw)
+        qo, _ = other.align(d["bgr_prev"], d["depth_prev"].copy(), d["bgr_cur"], d["depth_cur"].copy())
+        assert np.abs(qo - q3).max() < 5e-6, kw
+    for j in range(3):   # and the known motion is recovered
+        assert np.abs(m.Se3.from_qt(q3[j]).log().reshape(6) - d["xi"][j]).max() < 2e-4
+
+
+def test_init_guess_levels_extremes_vs_oracle(dvo_mod):
+    """init_guess is honoured like the reference does (estimate = init_guess.copy(), base_robust_dvo.py:149) with
+    one level and with five; the maximum of eight levels (coarsest level 2x2 pixels, where the normal equations
+    are degenerate and the reference's own result is noise) must run and either return a finite pose or None."""
+    from dense_visual_odometry_b200.synthetic import make_pairs_numpy
+    m = dvo_mod
+    d = make_pairs_numpy([21], height=512, width=512)
+    Km = _Km(d["K"])
+    xi0 = (0.5 * d["xi"][0]).astype(np.float32).reshape(6, 1)
+    for levels in (1, 5):
+        est = _estimator(m, d["K"], d["depth_scale"], levels, max_iterations=30)
+        est.step(d["bgr_prev"][0], d["depth_prev"][0].copy())
+        T = est.step(d["bgr_cur"][0], d["depth_cur"][0].copy(), init_guess=m.Se3.from_se3(xi0))
+        ref = O.OracleDVO(Km, d["depth_scale"], levels, max_iterations=30)
+        ref.step(d["bgr_prev"][0], d["depth_prev"][0].copy())
+        Tr = ref.step(d["bgr_cur"][0], d["depth_cur"][0].copy(), init_guess=O.pose_from_xi(xi0.reshape(6)))
+        print("levels", levels, est.last_stats["iters"][0][:levels].tolist(), ref.last_result.iters)
+        assert T is not None
+        assert np.abs(T.so3.quat.reshape(4) - Tr.q).max() < POSE_TOL and np.abs(T.tvec.reshape(3) - Tr.t).max() < POSE_TOL
+    d = make_pairs_numpy([22], height=256, width=256)
+    est = _estimator(m, d["K"], d["depth_scale"], 8, max_iterations=10)
+    est.step(d["bgr_prev"][0], d["depth_prev"][0].copy())
+    T = est.step(d["bgr_cur"][0], d["depth_cur"][0].copy())
+    assert T is None or np.all(np.isfinite(m.pose_to_qt(T)))
+    assert est._h.level_shape(7) == (2, 2)

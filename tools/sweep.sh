@@ -1,9 +1,21 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-for cfg in "--threads 128"; do
-python bench.py --steps 3 --warmup 3 --no-cpu --e2e-steps 2 --pairs 2048 $cfg 2>&1 | tail -1 | python -c "
-import sys,json
-for l in sys.stdin:
-    if l.startswith('{'):
-        d=json.loads(l); print(\"cfg $cfg\", \"value\", round(d[\"value\"]), 'ms_per_step', round(d['ms_per_step'],2), \"kernel_ms\", round(d[\"roofline\"][\"kernel_ms\"],2), \"frac\", round(d[\"roofline\"][\"frac\"],4), 'e2e', round(d['e2e']['value']), d[\"accuracy\"][\"max_abs_twist_error_vs_truth\"])
-"
-done
+python - <<'PY'
+import sys, time
+sys.path.insert(0, '.')
+import numpy as np, torch
+import dense_visual_odometry_b200 as m
+from dense_visual_odometry_b200.synthetic import make_pairs_torch, TUM_FR1, TUM_DEPTH_SCALE
+B=2048
+dev=torch.device('cuda',0)
+Km=np.array([[TUM_FR1[0],0,TUM_FR1[2]],[0,TUM_FR1[1],TUM_FR1[3]],[0,0,1]],dtype=np.float32)
+cam=m.RGBDCameraModel(Km,TUM_DEPTH_SCALE)
+d=make_pairs_torch(range(B),dev)
+hb=[torch.empty(d[k].shape,dtype=d[k].dtype).pin_memory() for k in ("bgr_prev","depth_prev","bgr_cur","depth_cur")]
+for h,k in zip(hb,("bgr_prev","depth_prev","bgr_cur","depth_cur")): h.copy_(d[k])
+al=m.PairBatchAligner(cam,480,640,4,max_pairs=B)
+for chunk in (128,256,512,1024):
+    al.align(*hb,chunk_pairs=chunk)
+    t0=time.perf_counter()
+    for _ in range(3): al.align(*hb,chunk_pairs=chunk)
+    dt=(time.perf_counter()-t0)/3
+    print('chunk',chunk,'e2e pose/s',round(B/dt),'GB/s',round(sum(h.numel()*h.element_size() for h in hb)/dt/1e9,1))
+PY
