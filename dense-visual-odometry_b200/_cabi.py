@@ -49,6 +49,8 @@ SYMBOLS = {
     "dvo_build_pyramids": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, _P]),
     "dvo_build_pyramids_gray": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, _P]),
     "dvo_build_pyramids_host": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, _P]),
+    "dvo_upload_frames": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P]),
+    "dvo_build_pyramids_staged": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
     "dvo_depth_clamp_threshold": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "dvo_estimate": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "dvo_estimate_host": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),

@@ -397,24 +397,46 @@ extern "C" int dvo_build_pyramids_gray(dvo_handle* h, int frame_base, const uint
                       false, (cudaStream_t)stream);
 }
 
-extern "C" int dvo_build_pyramids_host(dvo_handle* h, int frame_base, const uint8_t* bgr_host,
-                                       const uint16_t* depth_host, int n_frames, int with_gradients, void* stream) {
-    if (!h) return DVO_ERR_INVALID;
-    if (!bgr_host || !depth_host) return fail(h, DVO_ERR_INVALID, "null image pointer");
+static int stage_ready(dvo_handle* h, int frame_base, int n_frames) {
     if (n_frames < 1 || frame_base < 0 || frame_base + n_frames > h->max_frames)
         return fail(h, DVO_ERR_RANGE, "frame slots out of range");
     DVO_CUDA(h, cudaSetDevice(h->device));
-    const size_t px = (size_t)h->H * h->W;
     if (!h->stage_bgr) {
+        const size_t px = (size_t)h->H * h->W;
         DVO_CUDA(h, cudaMalloc(&h->stage_bgr, px * 3 * h->max_frames));
         DVO_CUDA(h, cudaMalloc(&h->stage_depth, px * sizeof(uint16_t) * h->max_frames));
     }
+    return DVO_OK;
+}
+
+extern "C" int dvo_upload_frames(dvo_handle* h, int frame_base, const uint8_t* bgr_host, const uint16_t* depth_host,
+                                 int n_frames, void* stream) {
+    if (!h) return DVO_ERR_INVALID;
+    if (!bgr_host || !depth_host) return fail(h, DVO_ERR_INVALID, "null image pointer");
+    const int rc = stage_ready(h, frame_base, n_frames);
+    if (rc != DVO_OK) return rc;
+    const size_t px = (size_t)h->H * h->W;
     cudaStream_t st = (cudaStream_t)stream;
-    uint8_t* sb = h->stage_bgr + px * 3 * frame_base;
-    uint16_t* sd = h->stage_depth + px * frame_base;
-    DVO_CUDA(h, cudaMemcpyAsync(sb, bgr_host, px * 3 * n_frames, cudaMemcpyHostToDevice, st));
-    DVO_CUDA(h, cudaMemcpyAsync(sd, depth_host, px * sizeof(uint16_t) * n_frames, cudaMemcpyHostToDevice, st));
-    return build_impl(h, frame_base, sb, sd, n_frames, with_gradients, true, true, st);
+    DVO_CUDA(h, cudaMemcpyAsync(h->stage_bgr + px * 3 * frame_base, bgr_host, px * 3 * n_frames, cudaMemcpyHostToDevice, st));
+    DVO_CUDA(h, cudaMemcpyAsync(h->stage_depth + px * frame_base, depth_host, px * sizeof(uint16_t) * n_frames,
+                                cudaMemcpyHostToDevice, st));
+    return DVO_OK;
+}
+
+extern "C" int dvo_build_pyramids_staged(dvo_handle* h, int frame_base, int n_frames, int with_gradients, void* stream) {
+    if (!h) return DVO_ERR_INVALID;
+    const int rc = stage_ready(h, frame_base, n_frames);
+    if (rc != DVO_OK) return rc;
+    const size_t px = (size_t)h->H * h->W;
+    return build_impl(h, frame_base, h->stage_bgr + px * 3 * frame_base, h->stage_depth + px * frame_base, n_frames,
+                      with_gradients, true, true, (cudaStream_t)stream);
+}
+
+extern "C" int dvo_build_pyramids_host(dvo_handle* h, int frame_base, const uint8_t* bgr_host,
+                                       const uint16_t* depth_host, int n_frames, int with_gradients, void* stream) {
+    const int rc = dvo_upload_frames(h, frame_base, bgr_host, depth_host, n_frames, stream);
+    if (rc != DVO_OK) return rc;
+    return dvo_build_pyramids_staged(h, frame_base, n_frames, with_gradients, stream);
 }
 
 extern "C" int dvo_get_pyramid(dvo_handle* h, int slot, int level, uint8_t* gray_dev, uint16_t* depth_dev,

@@ -420,9 +420,10 @@ class PairBatchAligner:
         return self._pin_qt[:B].numpy().copy(), stats_to_numpy(self._pin_stats[:B].numpy())
 
     def align(self, bgr_prev, depth_prev, bgr_cur, depth_cur, init_qt=None, chunk_pairs: int = 256):
-        """build() + estimate().  Host inputs are pipelined: the batch is cut into chunks of `chunk_pairs` pairs
-        that go round-robin over three streams, so the host->device copy of a chunk overlaps the pyramids and the
-        Gauss-Newton kernel of the chunks before it (kernels of different chunks share the GPU).  The result does
+        """build() + estimate().  Host inputs are pipelined: the batch is cut into chunks of `chunk_pairs` pairs;
+        one stream uploads chunk after chunk, three compute streams take the chunks round-robin, each waiting for
+        its upload and then building the pyramids and running the Gauss-Newton kernel while later chunks are still
+        on the bus (kernels of different chunks share the GPU).  The result does
         not depend on the chunking: every pair is estimated by one CTA with a fixed order of operations."""
         host = isinstance(bgr_prev, np.ndarray) or not bgr_prev.is_cuda
         B = bgr_prev.shape[0]
@@ -439,15 +440,27 @@ class PairBatchAligner:
             self._init = init_dev
         if not hasattr(self, "_streams"):
             self._streams = [torch.cuda.Stream(self._dev) for _ in range(3)]
+            self._copy_stream = torch.cuda.Stream(self._dev)
         cur = torch.cuda.current_stream(self._dev)
+        cs = self._copy_stream
+        cs.wait_stream(cur)
         for s in self._streams:
             s.wait_stream(cur)
+        cp = C.c_void_p(cs.cuda_stream)
+        # all uploads go back to back on one stream (the copy engine never idles); chunk k's compute stream
+        # waits for its upload's event, then builds and estimates while later chunks are still arriving.  Staging
+        # slots are per frame, so chunks of one call never share them; the previous call was synchronised.
         for k, lo in enumerate(range(0, B, chunk_pairs)):
             n = min(chunk_pairs, B - lo)
             s = self._streams[k % 3]
             sp = C.c_void_p(s.cuda_stream)
-            self._h.call("dvo_build_pyramids_host", lo, self._ptr(bp[lo]), self._ptr(dp[lo]), n, self._prev_grad, sp)
-            self._h.call("dvo_build_pyramids_host", self.max_pairs + lo, self._ptr(bc[lo]), self._ptr(dc[lo]), n, 1, sp)
+            self._h.call("dvo_upload_frames", lo, self._ptr(bp[lo]), self._ptr(dp[lo]), n, cp)
+            self._h.call("dvo_upload_frames", self.max_pairs + lo, self._ptr(bc[lo]), self._ptr(dc[lo]), n, cp)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+            s.wait_event(ev)
+            self._h.call("dvo_build_pyramids_staged", lo, n, self._prev_grad, sp)
+            self._h.call("dvo_build_pyramids_staged", self.max_pairs + lo, n, 1, sp)
             init_ptr = self._ptr(init_dev[lo]) if init_dev is not None else None
             self._h.call("dvo_estimate", lo, self.max_pairs + lo, n, init_ptr, None, self._ptr(self._qt[lo]),
                          self._ptr(self._stats[lo]), sp)
@@ -457,6 +470,7 @@ class PairBatchAligner:
         for s in self._streams:
             s.synchronize()
             cur.wait_stream(s)
+        cur.wait_stream(cs)
         self._B = B
         return self._pin_qt[:B].numpy().copy(), stats_to_numpy(self._pin_stats[:B].numpy())
 
@@ -498,6 +512,7 @@ class SequenceAligner:
         self._pin_qt = torch.empty((n, 7), dtype=torch.float32).pin_memory()
         self._pin_stats = torch.empty((n, _cabi.STATS_BYTES), dtype=torch.uint8).pin_memory()
         self._streams = [torch.cuda.Stream(self._dev) for _ in range(3)]
+        self._copy_stream = torch.cuda.Stream(self._dev)
 
     @property
     def handle(self) -> _Handle:
@@ -515,16 +530,27 @@ class SequenceAligner:
             bgr = (torch.as_tensor(bgr) if isinstance(bgr, np.ndarray) else bgr).contiguous()
             depth = (torch.as_tensor(depth) if isinstance(depth, np.ndarray) else depth).contiguous()
             self._keep = (bgr, depth)
-        build = "dvo_build_pyramids_host" if host else "dvo_build_pyramids"
         cur = torch.cuda.current_stream(self._dev)
+        cs = self._copy_stream
+        cs.wait_stream(cur)
         for s in self._streams:
             s.wait_stream(cur)
+        cp = C.c_void_p(cs.cuda_stream)
         built = None  # event: the previous chunk's pyramids are complete
         for k, lo in enumerate(range(0, N, chunk_frames)):
             hi = min(lo + chunk_frames, N)
             s = self._streams[k % 3]
             sp = C.c_void_p(s.cuda_stream)
-            self._h.call(build, lo, C.c_void_p(bgr[lo].data_ptr()), C.c_void_p(depth[lo].data_ptr()), hi - lo, 1, sp)
+            if host:   # uploads back to back on the copy stream, compute streams wait for their chunk's event
+                self._h.call("dvo_upload_frames", lo, C.c_void_p(bgr[lo].data_ptr()), C.c_void_p(depth[lo].data_ptr()),
+                             hi - lo, cp)
+                up = torch.cuda.Event()
+                up.record(cs)
+                s.wait_event(up)
+                self._h.call("dvo_build_pyramids_staged", lo, hi - lo, 1, sp)
+            else:
+                self._h.call("dvo_build_pyramids", lo, C.c_void_p(bgr[lo].data_ptr()), C.c_void_p(depth[lo].data_ptr()),
+                             hi - lo, 1, sp)
             ev = torch.cuda.Event()
             ev.record(s)
             p0, p1 = max(lo - 1, 0), hi - 1   # pairs whose current frame is in this chunk
@@ -540,6 +566,7 @@ class SequenceAligner:
         for s in self._streams:
             s.synchronize()
             cur.wait_stream(s)
+        cur.wait_stream(cs)
         return self._pin_qt[:N - 1].numpy().copy(), stats_to_numpy(self._pin_stats[:N - 1].numpy())
 
     def launch_count(self) -> int:

@@ -122,6 +122,12 @@ int dvo_build_pyramids_gray(dvo_handle* h, int frame_base, const uint8_t* gray_d
  * caller applies the reference's in-place clamp with dvo_depth_clamp_threshold if it needs it. */
 int dvo_build_pyramids_host(dvo_handle* h, int frame_base, const uint8_t* bgr_host, const uint16_t* depth_host,
                             int n_frames, int with_gradients, void* stream);
+/* The two halves of dvo_build_pyramids_host, for callers that keep the copy engine busy on a dedicated stream
+ * while other streams build and estimate (order them with events): upload = the two host->device copies into
+ * the staging area of slots frame_base.., staged = gray/clamp/pyramids/gradients from that staging area. */
+int dvo_upload_frames(dvo_handle* h, int frame_base, const uint8_t* bgr_host, const uint16_t* depth_host, int n_frames,
+                      void* stream);
+int dvo_build_pyramids_staged(dvo_handle* h, int frame_base, int n_frames, int with_gradients, void* stream);
 /* Smallest digital number d with (double)d * depth_scale > max_distance (65536 if none). */
 int dvo_depth_clamp_threshold(const dvo_handle* h, int* threshold);
 
