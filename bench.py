@@ -206,6 +206,7 @@ def gpu_arm(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep the version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     import dense_visual_odometry_b200 as dvo
