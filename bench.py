@@ -59,7 +59,7 @@ def _cpu_worker(args):
     d = make_pairs_numpy([seed], height=H, width=W)
     K = d["K"]
     Km = np.array([[K[0], 0, K[2]], [0, K[1], K[3]], [0, 0, 1]], dtype=np.float32)
-    wmode = {"none": O.W_NONE, "tdist": O.W_TDIST_REF, "huber": O.W_HUBER}[weights]
+    wmode = {"none": O.W_NONE, "tdist": O.W_TDIST_REF, "huber": O.W_HUBER, "huber_mad": O.W_HUBER_MAD}[weights]
     t0 = time.perf_counter()
     est = O.OracleDVO(Km, d["depth_scale"], LEVELS, weights=wmode, approximate_image2_gradient=approx)
     est.step(d["bgr_prev"][0], d["depth_prev"][0].copy())
@@ -279,6 +279,8 @@ def gpu_arm(args):
     extra = 0.0
     if args.weights == "tdist":   # + the residual pre-pass (4 B/px gathers + 4 B/px store) and one scale pass (4 B/px)
         extra = float((iters * np.array(px)[None, :]).sum() * 12)
+    elif args.weights == "huber_mad":   # + the residual pre-pass that feeds the median (I1 1 + D1 2 + I2 1 B/px)
+        extra = float((iters * np.array(px)[None, :]).sum() * 4)
     peak, peak_src = measured_peak()
     achieved = (algo_bytes + extra) / (kernel_ms / 1e3) / 1e9
 
@@ -385,7 +387,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=4096, help="frame pairs per GPU per step (BASELINE.json configs[3])")
-    ap.add_argument("--weights", default="none", choices=["none", "tdist", "huber"])
+    ap.add_argument("--weights", default="none", choices=["none", "tdist", "huber", "huber_mad"])
     ap.add_argument("--cpu-pairs", type=int, default=0,
                     help="pairs of the batch also estimated by the CPU oracle (0 = one per host core, at most 32)")
     ap.add_argument("--cpu-workers", type=int, default=0)

@@ -7,7 +7,7 @@ from pathlib import Path
 
 DVO_MAX_LEVELS = 8
 DVO_ACC_TERMS = 29
-W_NONE, W_TDIST_REF, W_HUBER = 0, 1, 2
+W_NONE, W_TDIST_REF, W_HUBER, W_HUBER_MAD = 0, 1, 2, 3
 OOB_INCLUSIVE, OOB_STRICT = 0, 1
 
 LIB_PATH = Path(__file__).resolve().parent / "libdvo_b200.so"

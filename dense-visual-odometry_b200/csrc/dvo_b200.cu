@@ -102,6 +102,10 @@ static align_fn pick_align(int w, int oob, int grad) {
     DVO_PICK(DVO_W_TDIST_REF, DVO_OOB_STRICT, 1)
     DVO_PICK(DVO_W_HUBER, DVO_OOB_INCLUSIVE, 1)
     DVO_PICK(DVO_W_HUBER, DVO_OOB_STRICT, 1)
+    DVO_PICK(DVO_W_HUBER_MAD, DVO_OOB_INCLUSIVE, 0)
+    DVO_PICK(DVO_W_HUBER_MAD, DVO_OOB_STRICT, 0)
+    DVO_PICK(DVO_W_HUBER_MAD, DVO_OOB_INCLUSIVE, 1)
+    DVO_PICK(DVO_W_HUBER_MAD, DVO_OOB_STRICT, 1)
 #endif
 #undef DVO_PICK
     return nullptr;

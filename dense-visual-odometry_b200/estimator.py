@@ -21,7 +21,7 @@ from .lie import Se3, pose_to_qt
 
 logger = logging.getLogger(__name__)
 
-_WEIGHTS = {"none": _cabi.W_NONE, "tdist": _cabi.W_TDIST_REF, "huber": _cabi.W_HUBER}
+_WEIGHTS = {"none": _cabi.W_NONE, "tdist": _cabi.W_TDIST_REF, "huber": _cabi.W_HUBER, "huber_mad": _cabi.W_HUBER_MAD}
 _OOB = {"inclusive": _cabi.OOB_INCLUSIVE, "strict": _cabi.OOB_STRICT}
 
 
@@ -113,6 +113,8 @@ def make_config(use_weighter=False, max_increased_steps_allowed=0, sigma=None, t
     cfg.sigma_prior = float(sigma) if sigma is not None else -1.0
     if huber_k is not None:
         cfg.huber_k = float(huber_k)
+    elif weights == "huber_mad":
+        cfg.huber_k = 1.345   # the tuning constant c of k = c * 1.4826 * MAD
     cfg.max_distance = float(max_distance)
     cfg.threads_per_block = int(threads_per_block)
     cfg.blocks_per_sm = int(blocks_per_sm)

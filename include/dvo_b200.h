@@ -46,7 +46,9 @@ typedef enum dvo_status {
 typedef enum dvo_weights {
     DVO_W_NONE = 0,      /* reference default, use_weighter=False (base_robust_dvo.py:182-184) */
     DVO_W_TDIST_REF = 1, /* reference TDistributionWeighter as written (weighter/t_weighter.py) */
-    DVO_W_HUBER = 2      /* extension, not in the reference: fixed-threshold Huber weights */
+    DVO_W_HUBER = 2,     /* extension, not in the reference: Huber weights, fixed threshold huber_k (intensity units) */
+    DVO_W_HUBER_MAD = 3  /* extension: Huber threshold huber_k * 1.4826 * median|r| re-estimated every iteration;
+                          * huber_k is then the tuning constant (1.345) */
 } dvo_weights;
 
 typedef enum dvo_oob_mode {

@@ -32,6 +32,7 @@ OOB_STRICT = 1     # valid iff x0 >= 0, y0 >= 0, x0+1 < W, y0+1 < H (docstring o
 W_NONE = 0
 W_TDIST_REF = 1    # weighter/t_weighter.py as written (scale is a SUM)
 W_HUBER = 2        # extension, parity unpinned
+W_HUBER_MAD = 3    # extension, parity unpinned: Huber threshold c * 1.4826 * MAD(r), re-estimated every iteration
 
 
 # --------------------------------------------------------------------------------------
@@ -475,6 +476,25 @@ def residuals_and_jacobian(ld: LevelData, T: np.ndarray, oob_mode: int = OOB_INC
     return r, J, ld.mask, valid
 
 
+MAD_BINS = 2048      # |r| is histogrammed in 1/8 intensity steps (covers [0, 256))
+MAD_BIN_SCALE = 8.0
+
+
+def huber_mad_threshold(r: np.ndarray, c: float = 1.345) -> float:
+    """Huber threshold from the residuals' median absolute value, as the CUDA kernel defines it: |r| is binned in
+    1/8 intensity steps, the LOWER median bin (the ceil(n/2)-th smallest value) is taken at its centre, and
+    k = c * 1.4826 * MAD, never below 1e-3.  Extension: the reference has no Huber weights (parity unpinned)."""
+    n = r.size
+    if n == 0:
+        return 1e-3
+    bins = np.minimum((np.abs(r.astype(F32)) * F32(MAD_BIN_SCALE)).astype(np.int64), MAD_BINS - 1)
+    hist = np.bincount(bins, minlength=MAD_BINS)
+    target = (n + 1) // 2
+    b = int(np.searchsorted(np.cumsum(hist), target, side="left"))
+    mad = F32((F32(b) + F32(0.5)) / F32(MAD_BIN_SCALE))
+    return float(max(F32(c) * F32(1.4826) * mad, F32(1e-3)))
+
+
 def normal_equations(r: np.ndarray, J: np.ndarray, weights: int = W_NONE, huber_k: float = 1.345 * 5.0,
                      tdist_kw: Optional[dict] = None):
     """base_robust_dvo.py:168-188.  Returns H (6,6) f32, b (6,) f32, err f32."""
@@ -486,6 +506,8 @@ def normal_equations(r: np.ndarray, J: np.ndarray, weights: int = W_NONE, huber_
         r2 = r * r
         if weights == W_TDIST_REF:
             wgt = tdist_weights(r2, **(tdist_kw or {}))
+        elif weights == W_HUBER_MAD:
+            wgt = huber_weights(r, huber_mad_threshold(r))
         else:
             wgt = huber_weights(r, huber_k)
         err = np.mean(wgt * r2) if r.size else F32(np.nan)
