@@ -227,8 +227,7 @@ def gpu_arm(args):
 
     al = dvo.PairBatchAligner(cam, H, W, LEVELS, max_pairs=B, device=local_rank, weights=args.weights,
                               threads_per_block=args.threads, blocks_per_sm=args.blocks_per_sm,
-                              prefetch_rows=args.prefetch_rows, approximate_image2_gradient=args.approximate_gradient,
-                              chunk_rows=args.chunk_rows)
+                              prefetch_rows=args.prefetch_rows, approximate_image2_gradient=args.approximate_gradient)
     from dense_visual_odometry_b200.sharding import gather_poses
 
     def step_resident():
@@ -396,7 +395,6 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--prefetch-rows", type=int, default=0)
-    ap.add_argument("--chunk-rows", type=int, default=0)
     ap.add_argument("--approximate-gradient", action="store_true",
                     help="the reference's approximate_image2_gradient=True mode (not the headline configuration)")
     args = ap.parse_args()

@@ -23,7 +23,7 @@ class dvo_config(C.Structure):
         ("sigma_prior", C.c_float), ("weights", C.c_int32), ("oob_mode", C.c_int32), ("tdist_dof", C.c_float),
         ("tdist_init_sigma", C.c_float), ("tdist_tolerance", C.c_float), ("tdist_max_iterations", C.c_int32),
         ("huber_k", C.c_float), ("max_distance", C.c_float), ("threads_per_block", C.c_int32),
-        ("blocks_per_sm", C.c_int32), ("approximate_image2_gradient", C.c_int32), ("cluster_size", C.c_int32), ("reserved", C.c_int32 * 2),
+        ("blocks_per_sm", C.c_int32), ("approximate_image2_gradient", C.c_int32), ("cluster_size", C.c_int32), ("tdist_mean", C.c_int32), ("reserved", C.c_int32 * 1),
     ]
 
 

@@ -478,8 +478,7 @@ static void fill_params(const dvo_handle* h, AlignParams& p) {
         g.h_magic = (unsigned)((1ull << 32) / (unsigned)h->lh[l]) + 1u;
         {   // chunks per strip = NW * k with about 60 rows per chunk (align_kernel.cuh, fused_pass)
             const int nw = h->threads / 32;
-            const int target = h->cfg.reserved[1] > 0 ? h->cfg.reserved[1] : 60;  // tuning knob: rows per chunk
-            int k = (h->lh[l] + nw * target / 2) / (nw * target);
+            int k = (h->lh[l] + nw * 30) / (nw * 60);
             if (k < 1) k = 1;
             g.chunks_per_strip = nw * k;
             g.chunk_rows = (h->lh[l] + g.chunks_per_strip - 1) / g.chunks_per_strip;
@@ -496,6 +495,7 @@ static void fill_params(const dvo_handle* h, AlignParams& p) {
     p.tdist_lambda0 = 1.0f / (h->cfg.tdist_init_sigma * h->cfg.tdist_init_sigma);
     p.tdist_tol = h->cfg.tdist_tolerance;
     p.tdist_max_iter = h->cfg.tdist_max_iterations;
+    p.tdist_mean = h->cfg.tdist_mean ? 1 : 0;
     p.huber_k = h->cfg.huber_k;
     const float s_hi = (float)h->depth_scale;
     p.scale_hi = s_hi;

@@ -21,7 +21,8 @@ from .lie import Se3, pose_to_qt
 
 logger = logging.getLogger(__name__)
 
-_WEIGHTS = {"none": _cabi.W_NONE, "tdist": _cabi.W_TDIST_REF, "huber": _cabi.W_HUBER, "huber_mad": _cabi.W_HUBER_MAD}
+_WEIGHTS = {"none": _cabi.W_NONE, "tdist": _cabi.W_TDIST_REF, "tdist_mean": _cabi.W_TDIST_REF, "huber": _cabi.W_HUBER,
+            "huber_mad": _cabi.W_HUBER_MAD}
 _OOB = {"inclusive": _cabi.OOB_INCLUSIVE, "strict": _cabi.OOB_STRICT}
 
 
@@ -95,7 +96,7 @@ class _Handle:
 def make_config(use_weighter=False, max_increased_steps_allowed=0, sigma=None, tolerance=1e-6, max_iterations=100,
                 weights: Optional[str] = None, oob_mode="inclusive", huber_k=None, max_distance=5.0,
                 threads_per_block=0, blocks_per_sm=0, prefetch_rows=0, approximate_image2_gradient=False,
-                cluster_size=0, chunk_rows=0):
+                cluster_size=0):
     lib = _cabi.load()
     cfg = _cabi.dvo_config()
     lib.dvo_default_config(C.byref(cfg))
@@ -106,6 +107,7 @@ def make_config(use_weighter=False, max_increased_steps_allowed=0, sigma=None, t
     if oob_mode not in _OOB:
         raise ValueError(f"oob_mode must be one of {list(_OOB)}, got '{oob_mode}'")
     cfg.weights = _WEIGHTS[weights]
+    cfg.tdist_mean = 1 if weights == "tdist_mean" else 0   # extension: textbook scale (mean), SURVEY F3
     cfg.oob_mode = _OOB[oob_mode]
     cfg.max_iterations = int(max_iterations)
     cfg.max_increased_steps = int(max_increased_steps_allowed)
@@ -120,7 +122,6 @@ def make_config(use_weighter=False, max_increased_steps_allowed=0, sigma=None, t
     cfg.blocks_per_sm = int(blocks_per_sm)
     cfg.approximate_image2_gradient = 1 if approximate_image2_gradient else 0
     cfg.cluster_size = int(cluster_size)
-    cfg.reserved[1] = int(chunk_rows)     # tuning knob: target rows per work chunk (0 = default 60)
     cfg.reserved[0] = int(prefetch_rows)  # tuning knob: L1 prefetch distance in rows (0 = default, < 0 = off, <= 32)
     return cfg
 

@@ -387,14 +387,17 @@ def pose_from_xi(xi: np.ndarray) -> Pose:
 # a12: reference t-distribution weighter                        weighter/t_weighter.py
 # --------------------------------------------------------------------------------------
 def tdist_lambda(r2: np.ndarray, dof: float = 5.0, init_sigma: float = 5.0, tol: float = 1e-3,
-                 max_iter: int = 50) -> float:
+                 max_iter: int = 50, mean: bool = False) -> float:
     """TDistributionWeighter.weight's fixed point (t_weighter.py:21-34) with the SUMMED scale
-    of `_compute_scale` (t_weighter.py:36-47).  Returns the final lambda."""
+    of `_compute_scale` (t_weighter.py:36-47).  Returns the final lambda.
+    mean=True is the textbook scale (an extension, parity unpinned): the mean instead of the sum."""
     r2 = r2.astype(np.float64).reshape(-1)
     last = 1.0 / (init_sigma ** 2)
     cur = last
     for _ in range(max_iter):
         sigma2 = float(np.sum(r2 * ((dof + 1) / (dof + r2 * last))))
+        if mean and r2.size:
+            sigma2 /= r2.size
         cur = 1.0 / sigma2 if sigma2 != 0 else float("inf")
         if abs(cur - last) < tol:
             break

@@ -678,3 +678,24 @@ def test_huber_mad_extension_vs_oracle(dvo_mod, golden_dir):
     r = (rng.standard_normal(10001) * 7).astype(np.float32)
     k = O.huber_mad_threshold(r)
     assert abs(k - 1.345 * 1.4826 * np.median(np.abs(r))) < 1.345 * 1.4826 * 0.13
+
+
+def test_textbook_tdist_scale_extension_vs_oracle(dvo_mod, golden_dir):
+    """weights="tdist_mean": the t-distribution weights with the textbook scale (mean instead of the reference's
+    sum).  Extension, parity unpinned: checked against the oracle's restatement; unlike the reference's
+    version the weights actually vary (the result differs from the unweighted one)."""
+    m = dvo_mod
+    g = np.load(golden_dir / "pose_syn160.npz")
+    K = tuple(float(v) for v in g["K"])
+    Km = _Km(K)
+    cam = m.RGBDCameraModel(Km, float(g["depth_scale"]))
+    rep = lambda a: np.ascontiguousarray(np.repeat(a[..., None], 3, axis=-1))  # noqa: E731
+    al = m.PairBatchAligner(cam, 120, 160, 3, max_pairs=1, weights="tdist_mean")
+    qt, stats = al.align(rep(g["gray_prev"][:1]), g["depth_prev"][:1].copy(), rep(g["gray_cur"][:1]),
+                         g["depth_cur"][:1].copy())
+    res = O.estimate_pose(Km, float(g["depth_scale"]), O.build_pyramid(g["gray_prev"][0], 3),
+                          O.build_pyramid(g["depth_prev"][0], 3), O.build_pyramid(g["gray_cur"][0], 3), 3,
+                          weights=O.W_TDIST_REF, tdist_kw={"mean": True})
+    print("iters", stats["iters"][0][:3].tolist(), res.iters)
+    assert np.abs(qt[0, :4] - res.pose.q).max() < POSE_TOL and np.abs(qt[0, 4:] - res.pose.t).max() < POSE_TOL
+    assert np.abs(qt[0, 4:] - g["p0_tdist_t"]).max() > 1e-6     # not the reference's constant-weight behaviour
