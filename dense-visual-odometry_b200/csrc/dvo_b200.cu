@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -505,6 +506,7 @@ static void fill_params(const dvo_handle* h, AlignParams& p) {
     p.scratch_stride = h->scratch_stride;
     // tuning knob (dvo_config.reserved[0]): L1 prefetch distance in rows; 0 = default (2), < 0 = off
     p.prefetch_rows = h->cfg.reserved[0] > 0 ? h->cfg.reserved[0] : (h->cfg.reserved[0] < 0 ? 0 : 2);
+    p.prefetch_raw_rows = p.prefetch_rows;
 }
 
 extern "C" int dvo_estimate(dvo_handle* h, int prev_base, int cur_base, int n_pairs, const float* init_qt_dev,
