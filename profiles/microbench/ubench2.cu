@@ -23,7 +23,8 @@ __device__ __forceinline__ float fsel(float a, float b, float c) { float d; asm 
 __device__ __forceinline__ unsigned isel(unsigned a, unsigned b, unsigned c) { unsigned d; asm volatile("{.reg .pred p; setp.le.u32 p, %3, %2; selp.u32 %0, %1, %2, p;}" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
 
 enum { FFMA, FFMA2, FMUL2, FADD2, FADD2RM, FADDRM, LOP, IADD, IMAD, PRMT, FSETP_SEL, ISETP_SEL, RCP, SHFL, F2I_FLOOR, I2F,
-       MIX_FFMA2_LOP, MIX_FFMA2_FFMA, MIX_FFMA2_IMAD, MIX_FFMA_LOP, MIX_FFMA2_LOP_2to1, MIX_KERNELISH };
+       MIX_FFMA2_LOP, MIX_FFMA2_FFMA, MIX_FFMA2_IMAD, MIX_FFMA_LOP, MIX_FFMA2_LOP_2to1, MIX_KERNELISH,
+       MIX_FFMA2_I2F, MIX_FFMA2_PRMT, MIX_FFMA2_FSEL, MIX_FFMA2_IADD, MIX_FFMA2_RCP, MIX_FFMA2_IMADWIDE, MIX_FFMA2_SHF };
 
 // N independent chains per thread; every op depends only on its own chain.
 template <int OP, int N>
@@ -61,6 +62,13 @@ __global__ void k(float* out, int iters, float b, float c) {
             if (OP == MIX_FFMA2_IMAD) { p[i] = ffma2(p[i], b2, c2); u[i] = imad(u[i], 3u, (unsigned)it); }
             if (OP == MIX_FFMA_LOP) { a[i] = ffma(a[i], b, c); u[i] = lop(u[i], 0x9e3779b9u); }
             if (OP == MIX_FFMA2_LOP_2to1) { p[i] = ffma2(p[i], b2, c2); p[i] = ffma2(p[i], c2, b2); u[i] = lop(u[i], 0x9e3779b9u); }
+            if (OP == MIX_FFMA2_I2F) { p[i] = ffma2(p[i], b2, c2); u[i] = __float_as_uint((float)(int)(u[i] & 0xffffu)) + it; }
+            if (OP == MIX_FFMA2_PRMT) { p[i] = ffma2(p[i], b2, c2); u[i] = prmt(u[i], 0x4B000000u, 0x7440u + (it & 1)); }
+            if (OP == MIX_FFMA2_FSEL) { p[i] = ffma2(p[i], b2, c2); a[i] = fsel(a[i], c, a[i]); }
+            if (OP == MIX_FFMA2_IADD) { p[i] = ffma2(p[i], b2, c2); u[i] = iadd(u[i], 0x9e3779b9u + it); }
+            if (OP == MIX_FFMA2_RCP) { p[i] = ffma2(p[i], b2, c2); a[i] = rcp(a[i]); }
+            if (OP == MIX_FFMA2_IMADWIDE) { p[i] = ffma2(p[i], b2, c2); u64 w; asm volatile("mad.wide.u32 %0, %1, 8, %2;" : "=l"(w) : "r"(u[i]), "l"((u64)it)); u[i] = (unsigned)w ^ (unsigned)(w >> 32); }
+            if (OP == MIX_FFMA2_SHF) { p[i] = ffma2(p[i], b2, c2); unsigned d; asm volatile("shf.l.wrap.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(u[i]), "r"(u[i]), "r"(it)); u[i] = d; }
             if (OP == MIX_KERNELISH) {  // per "pixel pair": 8 FFMA2/FMUL2, 3 FFMA, 3 ALU, 1 IMAD, 1 sel
                 p[i] = ffma2(p[i], b2, c2); p[i] = fmul2(p[i], b2); p[i] = ffma2(p[i], b2, c2); p[i] = fadd2(p[i], c2);
                 p[i] = ffma2(p[i], b2, c2); p[i] = fmul2(p[i], b2); p[i] = ffma2(p[i], b2, c2); p[i] = fadd2(p[i], c2);
@@ -130,6 +138,9 @@ int main() {
     R(RCP, 8, 1, 32); R(SHFL, 8, 1, 32); R(F2I_FLOOR, 8, 1, 32); R(I2F, 8, 1, 32);
     R(MIX_FFMA2_LOP, 8, 2, 32); R(MIX_FFMA2_FFMA, 8, 2, 32); R(MIX_FFMA2_IMAD, 8, 2, 32); R(MIX_FFMA_LOP, 8, 2, 32);
     R(MIX_FFMA2_LOP_2to1, 8, 3, 32); R(MIX_KERNELISH, 4, 16, 32);
+    // which pipe does an instruction share with FFMA2?  (2 instructions per chain step; ~3.6 = separate pipes, ~1.9 = same)
+    R(MIX_FFMA2_I2F, 8, 2, 32); R(MIX_FFMA2_PRMT, 8, 2, 32); R(MIX_FFMA2_FSEL, 8, 2, 32); R(MIX_FFMA2_IADD, 8, 2, 32);
+    R(MIX_FFMA2_RCP, 8, 2, 32); R(MIX_FFMA2_IMADWIDE, 8, 2, 32); R(MIX_FFMA2_SHF, 8, 2, 32);
     // occupancy / ILP sweep for the kernel-like mix and for FFMA2
     R(MIX_KERNELISH, 1, 16, 8); R(MIX_KERNELISH, 2, 16, 8); R(MIX_KERNELISH, 4, 16, 8);
     R(MIX_KERNELISH, 1, 16, 16); R(MIX_KERNELISH, 2, 16, 16); R(MIX_KERNELISH, 4, 16, 16);
