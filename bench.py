@@ -44,7 +44,7 @@ def level_pixels():
 # ------------------------------------------------------------------------------------------------ CPU side
 def _cpu_worker(args):
     """One pose estimate with the oracle port on one process (BLAS pinned to one thread)."""
-    seed, weights, approx = args
+    seed, weights, approx, depth = args
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
     os.environ.setdefault("MKL_NUM_THREADS", "1")
@@ -61,7 +61,8 @@ def _cpu_worker(args):
     Km = np.array([[K[0], 0, K[2]], [0, K[1], K[3]], [0, 0, 1]], dtype=np.float32)
     wmode = {"none": O.W_NONE, "tdist": O.W_TDIST_REF, "huber": O.W_HUBER, "huber_mad": O.W_HUBER_MAD}[weights]
     t0 = time.perf_counter()
-    est = O.OracleDVO(Km, d["depth_scale"], LEVELS, weights=wmode, approximate_image2_gradient=approx)
+    est = O.OracleDVO(Km, d["depth_scale"], LEVELS, weights=wmode, approximate_image2_gradient=approx,
+                      use_depth_residual=depth)
     est.step(d["bgr_prev"][0], d["depth_prev"][0].copy())
     T = est.step(d["bgr_cur"][0], d["depth_cur"][0].copy())
     dt = time.perf_counter() - t0
@@ -80,10 +81,10 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def run_cpu_sample(pool, seeds, weights, approx=False):
+def run_cpu_sample(pool, seeds, weights, approx=False, depth=False):
     """Estimates len(seeds) pairs in parallel; returns (pairs/s, results)."""
     t0 = time.perf_counter()
-    res = pool.map(_cpu_worker, [(s, weights, approx) for s in seeds])
+    res = pool.map(_cpu_worker, [(s, weights, approx, depth) for s in seeds])
     dt = time.perf_counter() - t0
     return len(seeds) / dt, res, dt
 
@@ -101,7 +102,7 @@ def reference_arm(args):
     try:
         for s in range(args.warmup + args.steps):
             seeds = [1000 * s + i for i in range(workers)]
-            v, _, dt = run_cpu_sample(pool, seeds, args.weights, args.approximate_gradient)
+            v, _, dt = run_cpu_sample(pool, seeds, args.weights, args.approximate_gradient, args.depth_residual)
             if s >= args.warmup:
                 times.append(dt)
     finally:
@@ -172,7 +173,8 @@ class ClockSampler:
 def workload_name(args):
     return (f"batch of independent synthetic 640x480 RGB-D pairs with known SE(3) motion (BASELINE.json configs[1] "
             f"pair type, batched as configs[3]), {LEVELS}-level pyramid, weights={args.weights}"
-            + (", approximate_image2_gradient" if getattr(args, "approximate_gradient", False) else ""))
+            + (", approximate_image2_gradient" if getattr(args, "approximate_gradient", False) else "")
+            + (", photometric + depth residual" if getattr(args, "depth_residual", False) else ""))
 
 
 def measured_peak():
@@ -227,7 +229,8 @@ def gpu_arm(args):
 
     al = dvo.PairBatchAligner(cam, H, W, LEVELS, max_pairs=B, device=local_rank, weights=args.weights,
                               threads_per_block=args.threads, blocks_per_sm=args.blocks_per_sm,
-                              prefetch_rows=args.prefetch_rows, approximate_image2_gradient=args.approximate_gradient)
+                              prefetch_rows=args.prefetch_rows, approximate_image2_gradient=args.approximate_gradient,
+                              use_depth_residual=args.depth_residual)
     from dense_visual_odometry_b200.sharding import gather_poses
 
     def step_resident():
@@ -280,6 +283,8 @@ def gpu_arm(args):
         extra = float((iters * np.array(px)[None, :]).sum() * 12)
     elif args.weights == "huber_mad":   # + the residual pre-pass that feeds the median (I1 1 + D1 2 + I2 1 B/px)
         extra = float((iters * np.array(px)[None, :]).sum() * 4)
+    if args.depth_residual:   # + D2 u16 per pixel per iteration; the separate pass re-reads D1 (not counted)
+        extra += float((iters * np.array(px)[None, :]).sum() * 2)
     peak, peak_src = measured_peak()
     achieved = (algo_bytes + extra) / (kernel_ms / 1e3) / 1e9
 
@@ -318,8 +323,10 @@ def gpu_arm(args):
         workers = max(1, min(cores, n_cpu))
         pool = cpu_pool(workers)
         try:
-            run_cpu_sample(pool, [base + i for i in range(workers)], args.weights, args.approximate_gradient)  # warm-up
-            v, res, dt = run_cpu_sample(pool, [base + i for i in range(n_cpu)], args.weights, args.approximate_gradient)
+            run_cpu_sample(pool, [base + i for i in range(workers)], args.weights, args.approximate_gradient,
+                           args.depth_residual)  # warm-up
+            v, res, dt = run_cpu_sample(pool, [base + i for i in range(n_cpu)], args.weights, args.approximate_gradient,
+                                        args.depth_residual)
         finally:
             pool.close()
         dmax = max(float(np.abs(r[1] - qt_h[r[0] - base]).max()) for r in res)
@@ -332,7 +339,8 @@ def gpu_arm(args):
     if rank == 0:
         # single-pair latency through the reference's own call, step(color, depth) with host arrays (cluster mode)
         est = dvo.get_dvo("robust-dvo", cam, dvo.Se3.identity(), levels=LEVELS, weights=args.weights,
-                          approximate_image2_gradient=args.approximate_gradient)
+                          approximate_image2_gradient=args.approximate_gradient,
+                          use_depth_residual=args.depth_residual)
         f0 = (bp[0].cpu().numpy(), dp[0].cpu().numpy())
         f1 = (bc[0].cpu().numpy(), dc[0].cpu().numpy())
         lat, kms = [], []
@@ -397,6 +405,8 @@ def main():
     ap.add_argument("--prefetch-rows", type=int, default=0)
     ap.add_argument("--approximate-gradient", action="store_true",
                     help="the reference's approximate_image2_gradient=True mode (not the headline configuration)")
+    ap.add_argument("--depth-residual", action="store_true",
+                    help="photometric + depth residual (extension, BASELINE.json configs[4]; not the headline configuration)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

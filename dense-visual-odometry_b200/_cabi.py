@@ -23,7 +23,8 @@ class dvo_config(C.Structure):
         ("sigma_prior", C.c_float), ("weights", C.c_int32), ("oob_mode", C.c_int32), ("tdist_dof", C.c_float),
         ("tdist_init_sigma", C.c_float), ("tdist_tolerance", C.c_float), ("tdist_max_iterations", C.c_int32),
         ("huber_k", C.c_float), ("max_distance", C.c_float), ("threads_per_block", C.c_int32),
-        ("blocks_per_sm", C.c_int32), ("approximate_image2_gradient", C.c_int32), ("cluster_size", C.c_int32), ("tdist_mean", C.c_int32), ("reserved", C.c_int32 * 1),
+        ("blocks_per_sm", C.c_int32), ("approximate_image2_gradient", C.c_int32), ("cluster_size", C.c_int32), ("tdist_mean", C.c_int32),
+        ("use_depth_residual", C.c_int32), ("depth_weight", C.c_float), ("reserved", C.c_int32 * 1),
     ]
 
 
@@ -55,6 +56,7 @@ SYMBOLS = {
     "dvo_estimate": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "dvo_estimate_host": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "dvo_residuals_jacobian": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "dvo_depth_residuals_jacobian": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
     "dvo_get_pyramid": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "dvo_level_shape": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "dvo_level_intrinsics": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float)]),

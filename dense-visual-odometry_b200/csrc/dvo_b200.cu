@@ -79,6 +79,7 @@ extern "C" void dvo_default_config(dvo_config* cfg) {
     cfg->tdist_max_iterations = 50;
     cfg->huber_k = 1.345f * 5.0f;
     cfg->max_distance = 5.0f;
+    cfg->depth_weight = 2500.0f;
 }
 
 extern "C" const char* dvo_last_error(const dvo_handle* h) { return h ? h->err.c_str() : kNullHandle; }
@@ -87,7 +88,19 @@ extern "C" const char* dvo_last_error(const dvo_handle* h) { return h ? h->err.c
 typedef void (*align_fn)(const AlignParams);
 
 template <int T, int B>
-static align_fn pick_align(int w, int oob, int grad) {
+static align_fn pick_align(int w, int oob, int grad, int depth) {
+    if (depth) {  // photometric + depth residual (extension): unweighted or fixed-threshold Huber photometric term
+#define DVO_PICKD(WM, OM) \
+    if (w == WM && oob == OM && grad == 0) return (align_fn)align_kernel<WM, OM, 0, T, B, 1>;
+#ifndef DVO_FAST_BUILD
+        DVO_PICKD(DVO_W_NONE, DVO_OOB_INCLUSIVE)
+        DVO_PICKD(DVO_W_NONE, DVO_OOB_STRICT)
+        DVO_PICKD(DVO_W_HUBER, DVO_OOB_INCLUSIVE)
+        DVO_PICKD(DVO_W_HUBER, DVO_OOB_STRICT)
+#endif
+#undef DVO_PICKD
+        return nullptr;
+    }
 #define DVO_PICK(WM, OM, GM) \
     if (w == WM && oob == OM && grad == GM) return (align_fn)align_kernel<WM, OM, GM, T, B>;
     DVO_PICK(DVO_W_NONE, DVO_OOB_INCLUSIVE, 0)
@@ -117,8 +130,9 @@ static align_fn pick_align(int w, int oob, int grad) {
 // shapes with more warps per SM spill inside the pipelined loop and measured slower (profiles/r1/SUMMARY.md).
 static align_fn get_align(const dvo_handle* h) {
     const int w = h->cfg.weights, o = h->cfg.oob_mode, gm = h->cfg.approximate_image2_gradient ? 1 : 0;
-    if (h->threads == 256) return pick_align<256, 1>(w, o, gm);
-    return pick_align<128, 2>(w, o, gm);
+    const int dz = h->cfg.use_depth_residual ? 1 : 0;
+    if (h->threads == 256) return pick_align<256, 1>(w, o, gm, dz);
+    return pick_align<128, 2>(w, o, gm, dz);
 }
 
 // Cluster-mode kernel (one thread-block cluster per pair); not built for the t-distribution weights.
@@ -240,7 +254,7 @@ static int create_impl(dvo_handle* h) {
     }
     align_fn fn = get_align(h);
     if (!fn) {
-        h->err = "unsupported weights / oob_mode / approximate_image2_gradient combination";
+        h->err = "unsupported weights / oob_mode / approximate_image2_gradient / use_depth_residual combination";
         return DVO_ERR_INVALID;
     }
     int occ = 0;
@@ -507,6 +521,7 @@ static void fill_params(const dvo_handle* h, AlignParams& p) {
     // tuning knob (dvo_config.reserved[0]): L1 prefetch distance in rows; 0 = default (2), < 0 = off
     p.prefetch_rows = h->cfg.reserved[0] > 0 ? h->cfg.reserved[0] : (h->cfg.reserved[0] < 0 ? 0 : 2);
     p.prefetch_raw_rows = p.prefetch_rows;
+    p.depth_weight = h->cfg.depth_weight;
 }
 
 extern "C" int dvo_estimate(dvo_handle* h, int prev_base, int cur_base, int n_pairs, const float* init_qt_dev,
@@ -534,7 +549,7 @@ extern "C" int dvo_estimate(dvo_handle* h, int prev_base, int cur_base, int n_pa
     DVO_CUDA(h, cudaMemsetAsync(p.queue, 0, sizeof(int), st));
     const int grid = n_pairs < h->grid_max ? n_pairs : h->grid_max;
     align_fn fn = get_align(h);
-    align_fn cfn = (h->cfg.cluster_size > 1) ? get_cluster(h) : nullptr;
+    align_fn cfn = (h->cfg.cluster_size > 1 && !h->cfg.use_depth_residual) ? get_cluster(h) : nullptr;
     DVO_CUDA(h, cudaEventRecord(h->ev0, st));
     void* args[] = {&p};
     if (cfn) {
@@ -614,6 +629,36 @@ extern "C" int dvo_residuals_jacobian(dvo_handle* h, int prev_slot, int cur_slot
     void* args[] = {&p, &level, &prev_slot, &cur_slot, &T12, &lambda, &r_dev, &J_dev, &depth_mask_dev,
                     &warp_valid_dev, &acc_dev};
     DVO_CUDA(h, cudaLaunchKernel((const void*)fn, dim3((n_tiles + 7) / 8), dim3(256), args, 0, st));
+    h->launches += 2;
+    return DVO_OK;
+}
+
+extern "C" int dvo_depth_residuals_jacobian(dvo_handle* h, int prev_slot, int cur_slot, int level, const float* qt_host,
+                                            float* rz_dev, float* Jz_dev, uint8_t* valid_dev, double* acc_dev,
+                                            void* stream) {
+    if (!h) return DVO_ERR_INVALID;
+    if (!qt_host) return fail(h, DVO_ERR_INVALID, "qt is null");
+    if (!h->intrinsics_set) return fail(h, DVO_ERR_STATE, "dvo_set_intrinsics must be called first");
+    if (prev_slot < 0 || prev_slot >= h->max_frames || cur_slot < 0 || cur_slot >= h->max_frames || level < 0 ||
+        level >= h->levels)
+        return fail(h, DVO_ERR_RANGE, "slot / level out of range");
+    DVO_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    AlignParams p;
+    fill_params(h, p);
+    DVO_CUDA(h, cudaMemcpyAsync(h->qt_one, qt_host, sizeof(float) * 7, cudaMemcpyHostToDevice, st));
+    pose_matrix_kernel<<<1, 1, 0, st>>>(h->qt_one, h->qt_one + 16);
+    if (acc_dev) DVO_CUDA(h, cudaMemsetAsync(acc_dev, 0, sizeof(double) * DVO_ACC_TERMS, st));
+    const int n_tiles = (int)(h->lplane[level] / kTile);
+    const float* T12 = h->qt_one + 16;
+    const dim3 grid((n_tiles + 7) / 8);
+    if (h->cfg.oob_mode == DVO_OOB_STRICT)
+        depth_dump_kernel<DVO_OOB_STRICT><<<grid, 256, 0, st>>>(p, level, prev_slot, cur_slot, T12, rz_dev, Jz_dev,
+                                                                valid_dev, acc_dev);
+    else
+        depth_dump_kernel<DVO_OOB_INCLUSIVE><<<grid, 256, 0, st>>>(p, level, prev_slot, cur_slot, T12, rz_dev, Jz_dev,
+                                                                   valid_dev, acc_dev);
+    DVO_CUDA(h, cudaGetLastError());
     h->launches += 2;
     return DVO_OK;
 }

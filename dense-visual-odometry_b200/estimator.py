@@ -96,7 +96,7 @@ class _Handle:
 def make_config(use_weighter=False, max_increased_steps_allowed=0, sigma=None, tolerance=1e-6, max_iterations=100,
                 weights: Optional[str] = None, oob_mode="inclusive", huber_k=None, max_distance=5.0,
                 threads_per_block=0, blocks_per_sm=0, prefetch_rows=0, approximate_image2_gradient=False,
-                cluster_size=0):
+                cluster_size=0, use_depth_residual=False, depth_weight=None):
     lib = _cabi.load()
     cfg = _cabi.dvo_config()
     lib.dvo_default_config(C.byref(cfg))
@@ -122,6 +122,10 @@ def make_config(use_weighter=False, max_increased_steps_allowed=0, sigma=None, t
     cfg.blocks_per_sm = int(blocks_per_sm)
     cfg.approximate_image2_gradient = 1 if approximate_image2_gradient else 0
     cfg.cluster_size = int(cluster_size)
+    # extension (parity unpinned): photometric + depth residual, lambda_Z = depth_weight
+    cfg.use_depth_residual = 1 if use_depth_residual else 0
+    if depth_weight is not None:
+        cfg.depth_weight = float(depth_weight)
     cfg.reserved[0] = int(prefetch_rows)  # tuning knob: L1 prefetch distance in rows (0 = default, < 0 = off, <= 32)
     return cfg
 
@@ -141,14 +145,16 @@ class RobustDVOB200:
     gpu_robust_dense_visual_odometry.py:17; if omitted the device state is created on the first frame).
     Extras, all defaulting to reference behaviour: `weights` ("none" | "tdist" | "huber"), `oob_mode`
     ("inclusive" | "strict"), `huber_k`, `max_distance`, `device`, `cluster_size` (CTAs sharing the
-    pair: 1, 2, 4, 8 or 16).
+    pair: 1, 2, 4, 8 or 16), `use_depth_residual` / `depth_weight` (photometric + depth residual, an extension the
+    reference does not have; with weights "none" or "huber").
     """
 
     def __init__(self, camera_model, initial_pose, levels: int, use_weighter: bool = False,
                  max_increased_steps_allowed: int = 0, sigma: float = None, tolerance: float = 1e-6,
                  max_iterations: int = 100, approximate_image2_gradient: bool = False, height: int = None,
                  width: int = None, weights: Optional[str] = None, oob_mode: str = "inclusive",
-                 huber_k: float = None, max_distance: float = 5.0, device: int = 0, cluster_size: int = 8):
+                 huber_k: float = None, max_distance: float = 5.0, device: int = 0, cluster_size: int = 8,
+                 use_depth_residual: bool = False, depth_weight: float = None):
         if levels < 1 or levels > _cabi.DVO_MAX_LEVELS:
             raise ValueError(f"levels must be in [1, {_cabi.DVO_MAX_LEVELS}], got {levels}")
         self._camera_model = camera_model
@@ -164,7 +170,8 @@ class RobustDVOB200:
         # 640x480 pose at 8); the t-distribution weights fall back to one 256-thread CTA
         self._cfg = make_config(use_weighter, max_increased_steps_allowed, sigma, tolerance, max_iterations, weights,
                                 oob_mode, huber_k, max_distance, threads_per_block=256,
-                                approximate_image2_gradient=approximate_image2_gradient, cluster_size=cluster_size)
+                                approximate_image2_gradient=approximate_image2_gradient, cluster_size=cluster_size,
+                                use_depth_residual=use_depth_residual, depth_weight=depth_weight)
         self._approx = bool(approximate_image2_gradient)
         self._h: Optional[_Handle] = None
         self._have_prev = False
@@ -332,6 +339,23 @@ class RobustDVOB200:
         torch.cuda.current_stream(self._dev).synchronize()
         return (r.cpu().numpy(), J.cpu().numpy(), m.cpu().numpy().astype(bool), v.cpu().numpy().astype(bool),
                 acc.cpu().numpy())
+
+    def depth_residuals_dense(self, estimate, level: int, prev_slot: int, cur_slot: int):
+        """Dense dump of the depth-residual extension at one level: r_Z [H,W] (NaN = undefined), J_Z [H,W,6],
+        valid_Z mask, acc[29] (float64: the term's share of the normal equations, depth_weight included)."""
+        torch = self._torch
+        hl, wl = self._h.level_shape(level)
+        st = _stream_ptr(torch, self._dev)
+        r = torch.empty((hl, wl), dtype=torch.float32, device=self._dev)
+        J = torch.empty((hl, wl, 6), dtype=torch.float32, device=self._dev)
+        v = torch.empty((hl, wl), dtype=torch.uint8, device=self._dev)
+        acc = torch.empty((_cabi.DVO_ACC_TERMS,), dtype=torch.float64, device=self._dev)
+        qt = np.ascontiguousarray(pose_to_qt(estimate))
+        self._h.call("dvo_depth_residuals_jacobian", prev_slot, cur_slot, level, qt.ctypes.data_as(C.c_void_p),
+                     C.c_void_p(r.data_ptr()), C.c_void_p(J.data_ptr()), C.c_void_p(v.data_ptr()),
+                     C.c_void_p(acc.data_ptr()), st)
+        torch.cuda.current_stream(self._dev).synchronize()
+        return r.cpu().numpy(), J.cpu().numpy(), v.cpu().numpy().astype(bool), acc.cpu().numpy()
 
     def get_pyramid_level(self, slot: int, level: int):
         """(gray u8, depth u16, gx f32, gy f32) of one level of a frame slot, as host arrays."""

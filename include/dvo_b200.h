@@ -81,6 +81,12 @@ typedef struct dvo_config {
                                   * pair (latency of single pairs and short batches); ignored with the t-dist and Huber/MAD weights */
     int32_t tdist_mean;          /* extension, with DVO_W_TDIST_REF only: 1 = the textbook t-distribution scale
                                   * (MEAN of the weighted squared residuals) instead of the reference's sum (default 0) */
+    int32_t use_depth_residual;  /* extension, not in the reference: 1 = add the depth (geometric) residual
+                                  * r_Z = Z2(w(x)) - [T P]_z to the normal equations with weight depth_weight; available
+                                  * with DVO_W_NONE / DVO_W_HUBER, approximate_image2_gradient = 0, one CTA per pair.
+                                  * default 0 */
+    float depth_weight;          /* lambda_Z: a depth residual of 1/sqrt(lambda_Z) metres weighs like one grey level.
+                                  * default 2500 (2 cm) */
     int32_t reserved[1];         /* tuning: [0] L1 prefetch distance in rows (0 default, < 0 off) */
 } dvo_config;
 
@@ -158,6 +164,14 @@ int dvo_estimate_host(dvo_handle* h, int prev_base, int cur_base, int n_pairs, c
 int dvo_residuals_jacobian(dvo_handle* h, int prev_slot, int cur_slot, int level, const float* qt_host,
                            float* r_dev, float* J_dev, uint8_t* depth_mask_dev, uint8_t* warp_valid_dev,
                            double* acc_dev, void* stream);
+
+/* Dense form of the depth-residual extension (dvo_config.use_depth_residual; no reference counterpart, defined in
+ * align_kernel.cuh / oracle depth_residuals_and_jacobian) for one pair at one level and one pose:
+ *   rz_dev [H_l*W_l] f32 metres (NaN where undefined), Jz_dev [H_l*W_l,6] f32, valid_dev [H_l*W_l] u8 (any may be
+ *   NULL); acc_dev [DVO_ACC_TERMS] f64 = the term's contribution to the normal equations, depth_weight included,
+ *   [28] = number of depth residuals.  Works whether or not the handle was created with use_depth_residual. */
+int dvo_depth_residuals_jacobian(dvo_handle* h, int prev_slot, int cur_slot, int level, const float* qt_host,
+                                 float* rz_dev, float* Jz_dev, uint8_t* valid_dev, double* acc_dev, void* stream);
 
 /* Reads back one pyramid level of a frame slot (ImagePyramid.at, image_pyramid.py:60-65, and the Sobel
  * planes of jacobian.py:70-71).  Outputs are dense [H_l,W_l]; any may be NULL. */

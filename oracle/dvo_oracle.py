@@ -435,9 +435,12 @@ class LevelData:
     Jw: np.ndarray = None
     i1: np.ndarray = None
     J_approx: np.ndarray = None  # approximate_image2_gradient: Jacobian fixed per level, from I1's gradients
+    depth_cur: np.ndarray = None  # depth-residual extension only: the current frame's depth level (u16)
+    depth_scale: float = 0.0
 
 
-def prepare_level(K, depth_scale, gray_prev, depth_prev, gray_cur, level, approximate: bool = False) -> LevelData:
+def prepare_level(K, depth_scale, gray_prev, depth_prev, gray_cur, level, approximate: bool = False,
+                  depth_cur: Optional[np.ndarray] = None) -> LevelData:
     """_setup (cpu_...py:54-77) + the pose-independent part of compute_residuals_and_jacobian.
 
     approximate=True is the reference's `approximate_image2_gradient` mode (cpu_...py:60-77, :160-165): the image
@@ -446,6 +449,8 @@ def prepare_level(K, depth_scale, gray_prev, depth_prev, gray_cur, level, approx
     K_l = intrinsics_at(K, level)
     gx, gy = sobel3(gray_prev if approximate else gray_cur)
     ld = LevelData(K_l, gray_prev, depth_prev, gray_cur, gx, gy)
+    ld.depth_cur = depth_cur
+    ld.depth_scale = depth_scale
     ld.P, ld.mask = deproject(depth_prev, K_l, depth_scale)
     ld.Jw = warp_jacobian(ld.P, K_l)
     ld.i1 = gray_prev[ld.mask]
@@ -477,6 +482,51 @@ def residuals_and_jacobian(ld: LevelData, T: np.ndarray, oob_mode: int = OOB_INC
         J = (gxv[:, None] * Jw[:, 0, :] + gyv[:, None] * Jw[:, 1, :]).astype(F32)
     r = (i2[valid] - ld.i1[valid]).astype(F32)
     return r, J, ld.mask, valid
+
+
+def depth_residuals_and_jacobian(ld: LevelData, T: np.ndarray, oob_mode: int = OOB_INCLUSIVE):
+    """Depth (geometric) residual: an EXTENSION, the reference has none -- PARITY UNPINNED.  This is the
+    definition the CUDA kernel implements (align_kernel.cuh, depth_pair_math), in float64:
+
+      (u', v') = project(T P)  exactly as for the photometric term                      cpu_...py:173-176
+      valid_Z  = photometric-valid and u' < W-1 and v' < H-1 (no clamped tap) and the four taps of the current
+                 frame's depth level around (u', v') are non-zero
+      Z2       = scale * bilinear(D2)(u', v');   r_Z = Z2 - (T P)_z
+      grad Z2  = derivative of the bilinear patch: dZ/du = scale ((1-wy)(d10-d00) + wy (d11-d01)), dZ/dv likewise
+      J_Z      = [dZ/du dZ/dv] J_w - [0 0 1 Y -X 0], J_w and (X, Y) at the UNtransformed point, the reference's
+                 convention for the photometric Jacobian (utils/jacobian.py:37-40)
+
+    Returns r_Z (Nz,) f32, J_Z (Nz,6) f32, valid_Z (N,) bool over the depth-valid pixels in row-major order."""
+    Pw = np.dot(T.astype(F32), ld.P)
+    uv = project(Pw, ld.K)
+    x = uv[0].astype(F32)
+    y = uv[1].astype(F32)
+    h, w = ld.depth_cur.shape
+    i2 = interp_bilinear(ld.gray_cur, np.ascontiguousarray(uv[:2].T), oob_mode)
+    with np.errstate(invalid="ignore"):
+        inside = ~np.isnan(i2) & (x < w - 1) & (y < h - 1)
+    xs = np.where(inside, x, 0).astype(np.float64)
+    ys = np.where(inside, y, 0).astype(np.float64)
+    x0 = np.floor(xs).astype(np.int64)
+    y0 = np.floor(ys).astype(np.int64)
+    wx = xs - x0
+    wy = ys - y0
+    D = ld.depth_cur.astype(np.float64)
+    d00, d10, d01, d11 = D[y0, x0], D[y0, x0 + 1], D[y0 + 1, x0], D[y0 + 1, x0 + 1]
+    valid = inside & (d00 != 0) & (d10 != 0) & (d01 != 0) & (d11 != 0)
+    sc = float(ld.depth_scale)
+    z2 = sc * ((1 - wx) * (1 - wy) * d00 + wx * (1 - wy) * d10 + (1 - wx) * wy * d01 + wx * wy * d11)
+    rz = z2 - Pw[2].astype(np.float64)
+    dzu = sc * ((1 - wy) * (d10 - d00) + wy * (d11 - d01))
+    dzv = sc * ((1 - wx) * (d01 - d00) + wx * (d11 - d10))
+    Jw = ld.Jw.astype(np.float64)
+    J = dzu[:, None] * Jw[:, 0, :] + dzv[:, None] * Jw[:, 1, :]
+    X = ld.P[0].astype(np.float64)
+    Y = ld.P[1].astype(np.float64)
+    J[:, 2] -= 1.0
+    J[:, 3] -= Y
+    J[:, 4] += X
+    return rz[valid].astype(F32), J[valid].astype(F32), valid
 
 
 MAD_BINS = 2048      # |r| is histogrammed in 1/8 intensity steps (covers [0, 256))
@@ -547,8 +597,13 @@ def estimate_pose(K, depth_scale, gray_prev_pyr, depth_prev_pyr, gray_cur_pyr, l
                   max_increased_steps_allowed: int = 0, sigma: Optional[float] = None,
                   last_transform: Optional[Pose] = None, oob_mode: int = OOB_INCLUSIVE,
                   huber_k: float = 1.345 * 5.0, tdist_kw: Optional[dict] = None,
-                  approximate_image2_gradient: bool = False) -> EstimateResult:
-    """BaseRobustDVO._step (base_robust_dvo.py:137-236): coarse-to-fine Gauss-Newton."""
+                  approximate_image2_gradient: bool = False, depth_cur_pyr=None,
+                  depth_weight: float = 2500.0) -> EstimateResult:
+    """BaseRobustDVO._step (base_robust_dvo.py:137-236): coarse-to-fine Gauss-Newton.
+
+    depth_cur_pyr (extension, parity unpinned): the current frame's depth pyramid; when given, the depth term of
+    depth_residuals_and_jacobian joins the normal equations: H += lambda J_Z^T J_Z, b -= lambda J_Z^T r_Z and
+    err += lambda sum r_Z^2 / n with n the photometric residual count."""
     est = (init or Pose()).copy()
     iters = [0] * levels
     err_last = [float("nan")] * levels
@@ -559,10 +614,17 @@ def estimate_pose(K, depth_scale, gray_prev_pyr, depth_prev_pyr, gray_cur_pyr, l
         err_prev = np.finfo("float32").max
         inc_count = 0
         ld = prepare_level(K, depth_scale, gray_prev_pyr[level], depth_prev_pyr[level], gray_cur_pyr[level], level,
-                           approximate_image2_gradient)
+                           approximate_image2_gradient,
+                           depth_cur_pyr[level] if depth_cur_pyr is not None else None)
         for i in range(max_iterations):
             r, J, _, valid = residuals_and_jacobian(ld, est.matrix(), oob_mode)
             H, b, err = normal_equations(r, J, weights, huber_k, tdist_kw)
+            if depth_cur_pyr is not None:
+                rz, Jz, _ = depth_residuals_and_jacobian(ld, est.matrix(), oob_mode)
+                lam = F32(depth_weight)
+                H = (H + lam * (Jz.T @ Jz)).astype(F32)
+                b = (b - lam * (Jz.T @ rz)).astype(F32)
+                err = F32(err + lam * F32(np.sum(rz.astype(np.float64) ** 2)) / F32(max(r.size, 1)))
             if sigma is not None:
                 inv_cov = (1 / sigma) * np.eye(6, dtype=F32)
                 H = H + inv_cov
@@ -596,7 +658,9 @@ class OracleDVO:
     def __init__(self, K, depth_scale, levels, initial_pose: Optional[Pose] = None, use_weighter=False,
                  max_increased_steps_allowed=0, sigma=None, tolerance=1e-6, max_iterations=100,
                  max_distance=5.0, oob_mode=OOB_INCLUSIVE, weights: Optional[int] = None, huber_k=1.345 * 5.0,
-                 approximate_image2_gradient=False):
+                 approximate_image2_gradient=False, use_depth_residual=False, depth_weight=2500.0):
+        self.use_depth_residual = use_depth_residual
+        self.depth_weight = depth_weight
         self.K = np.asarray(K, dtype=F32)[:3, :3]
         self.depth_scale = depth_scale
         self.levels = levels
@@ -620,7 +684,9 @@ class OracleDVO:
             res = estimate_pose(self.K, self.depth_scale, build_pyramid(self._gray_prev, self.levels),
                                 build_pyramid(self._depth_prev, self.levels), build_pyramid(gray, self.levels),
                                 self.levels, init=init_guess, weights=self.weights, last_transform=self._last,
-                                **self.kw)
+                                depth_cur_pyr=(build_pyramid(depth_image, self.levels)
+                                               if self.use_depth_residual else None),
+                                depth_weight=self.depth_weight, **self.kw)
             self.last_result = res
             T = res.pose
         self._last = T.copy()
