@@ -203,3 +203,64 @@ def make_pairs_torch(seeds, device, height=480, width=640, K=TUM_FR1, depth_scal
         ts += [s.t for s in scenes]
     return dict(bgr_prev=bgr_prev, depth_prev=depth_prev, bgr_cur=bgr_cur, depth_cur=depth_cur,
                 xi=np.stack(xis).astype(np.float64), R=np.stack(Rs), t=np.stack(ts), K=Ks, depth_scale=depth_scale)
+
+
+def make_sequence_motions(n_frames: int, seed: int = 1000, trans_mag: float = 0.02, rot_mag: float = 0.01,
+                          smooth: float = 0.8):
+    """Frame-to-frame twists of a smooth trajectory: AR(1)-smoothed draws of the same
+    magnitude as the pair generator's.  Returns (xi_rel [n-1,6], R_abs [n,3,3], t_abs [n,3]) with
+    X_k = R_abs[k] X_0 + t_abs[k] and X_{k+1} = exp(xi_rel[k]) X_k."""
+    rng = np.random.default_rng(seed)
+    mag = np.concatenate([np.full(3, trans_mag), np.full(3, rot_mag)])
+    xi = rng.uniform(-1, 1, 6) * mag
+    xis = []
+    R_abs, t_abs = [np.eye(3)], [np.zeros(3)]
+    for _ in range(n_frames - 1):
+        xi = smooth * xi + (1 - smooth) * rng.uniform(-1, 1, 6) * mag
+        R, t = se3_exp(xi)
+        xis.append(xi.copy())
+        R_abs.append(R @ R_abs[-1])
+        t_abs.append(R @ t_abs[-1] + t)
+    return np.array(xis).reshape(-1, 6), np.stack(R_abs), np.stack(t_abs)
+
+
+def make_sequence(n_frames: int, device=None, height=480, width=640, K=TUM_FR1, depth_scale=TUM_DEPTH_SCALE,
+                  scene_seed: int = 1000, motion_seed: int = 1000, chunk: int = 32, hole_frac: float = 0.10,
+                  **motion_kw):
+    """A stream of `n_frames` views of ONE textured plane along a smooth trajectory (BASELINE.json configs[2]).
+    device=None renders with NumPy (host arrays), otherwise with torch on that device (tensors stay there).
+    Returns dict(bgr [N,H,W,3] u8, depth [N,H,W] u16, xi [N-1,6] = the twist taking frame k's camera to frame k+1's,
+    K, depth_scale).  Every frame gets its own 8x8-block depth holes."""
+    scale = width / 640.0
+    Ks = (K[0] * scale, K[1] * scale, K[2] * scale, K[3] * scale)
+    base = make_scene(scene_seed, height, width, Ks[0], hole_frac=hole_frac)
+    xi_rel, R_abs, t_abs = make_sequence_motions(n_frames, motion_seed, **motion_kw)
+    rng = np.random.default_rng(motion_seed + 7)
+    hb, wb = (height + 7) // 8, (width + 7) // 8
+    if device is None:
+        xp = np
+        bgr = np.empty((n_frames, height, width, 3), np.uint8)
+        depth = np.empty((n_frames, height, width), np.uint16)
+    else:
+        import torch
+        xp = torch
+        bgr = torch.empty((n_frames, height, width, 3), dtype=torch.uint8, device=device)
+        depth = torch.empty((n_frames, height, width), dtype=torch.uint16, device=device)
+    for c0 in range(0, n_frames, chunk):
+        n = min(chunk, n_frames - c0)
+        rep = lambda a: np.stack([np.asarray(a)] * n)  # noqa: E731
+        arrays = (rep(base.normal), np.full(n, base.offset), rep(base.e1), rep(base.e2), rep(base.freq),
+                  rep(base.phase), rep(base.amp), R_abs[c0:c0 + n], t_abs[c0:c0 + n])
+        _, _, g2, d2, _ = _render(xp, arrays, height, width, Ks, depth_scale, device=device)
+        holes = np.stack([np.kron(rng.random((hb, wb)) < hole_frac, np.ones((8, 8), dtype=bool))[:height, :width]
+                          for _ in range(n)])
+        if device is None:
+            d = d2.astype(np.uint16)
+            d[holes] = 0
+            depth[c0:c0 + n] = d
+            bgr[c0:c0 + n] = g2.astype(np.uint8)[..., None]
+        else:
+            d = d2.to(xp.int32).masked_fill(xp.as_tensor(holes, device=device), 0)
+            depth[c0:c0 + n] = d.to(xp.uint16)
+            bgr[c0:c0 + n] = g2.to(xp.uint8)[..., None]
+    return dict(bgr=bgr, depth=depth, xi=xi_rel.astype(np.float64), K=Ks, depth_scale=depth_scale)
