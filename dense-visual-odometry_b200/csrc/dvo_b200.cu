@@ -521,6 +521,14 @@ static void fill_params(const dvo_handle* h, AlignParams& p) {
     // tuning knob (dvo_config.reserved[0]): L1 prefetch distance in rows; 0 = default (2), < 0 = off
     p.prefetch_rows = h->cfg.reserved[0] > 0 ? h->cfg.reserved[0] : (h->cfg.reserved[0] < 0 ? 0 : 2);
     p.prefetch_raw_rows = p.prefetch_rows;
+    {   // residual-only passes run further ahead; developer knob DVO_TUNE_RES_PF (rows, 1..32)
+        static const int res_rows = [] {
+            const char* e = getenv("DVO_TUNE_RES_PF");
+            const int v = e ? atoi(e) : 0;
+            return (v >= 1 && v <= 32) ? v : 4;
+        }();
+        p.prefetch_res_rows = res_rows;
+    }
     p.depth_weight = h->cfg.depth_weight;
 }
 
