@@ -351,7 +351,7 @@ def gpu_arm(args):
             lat.append(1e3 * (time.perf_counter() - t0))
             kms.append(est._h.last_estimate_ms())
         latency = {"single_pair_step_ms": float(np.median(lat[2:])), "single_pair_kernel_ms": float(np.median(kms[2:])),
-                   "cluster_size": 8 if args.weights != "tdist" else 1,
+                   "cluster_size": 1 if (args.weights == "huber_mad" or args.depth_residual) else 8,
                    "note": "one 640x480 pair through get_dvo(...).step(color, depth): H2D of the frame, pyramids, "
                            "estimate on one thread-block cluster, D2H of the pose"}
     if rank == 0:

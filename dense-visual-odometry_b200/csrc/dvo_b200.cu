@@ -32,6 +32,7 @@ struct dvo_handle {
     int queue_next = 0;
     float* scratch = nullptr;
     size_t scratch_stride = 0;
+    int scratch_planes = 0;
     int sm_count = 0, threads = 256, blocks_per_sm = 2, grid_max = 0;
     uint8_t* stage_bgr = nullptr;
     uint16_t* stage_depth = nullptr;
@@ -47,6 +48,7 @@ struct dvo_handle {
 };
 
 static const int kQueueSlots = 256;
+static const int kClusterTdistMaxPairs = 256;  // cluster mode + t-distribution: one residual plane per pair
 static const int kScratchSets = 3;  // t-distribution residual planes for up to 3 estimate launches in flight
 static const char* kNullHandle = "null handle";
 
@@ -149,6 +151,10 @@ static align_fn get_cluster(const dvo_handle* h) {
     DVO_PICKC(DVO_W_NONE, DVO_OOB_STRICT, 1)
     DVO_PICKC(DVO_W_HUBER, DVO_OOB_INCLUSIVE, 1)
     DVO_PICKC(DVO_W_HUBER, DVO_OOB_STRICT, 1)
+    DVO_PICKC(DVO_W_TDIST_REF, DVO_OOB_INCLUSIVE, 0)
+    DVO_PICKC(DVO_W_TDIST_REF, DVO_OOB_STRICT, 0)
+    DVO_PICKC(DVO_W_TDIST_REF, DVO_OOB_INCLUSIVE, 1)
+    DVO_PICKC(DVO_W_TDIST_REF, DVO_OOB_STRICT, 1)
 #endif
 #undef DVO_PICKC
     return nullptr;
@@ -264,8 +270,12 @@ static int create_impl(dvo_handle* h) {
     h->grid_max = h->sm_count * h->blocks_per_sm;
     DVO_CUDA(h, cudaMalloc(&h->queue, sizeof(int) * kQueueSlots));
     if (h->cfg.weights == DVO_W_TDIST_REF) {
+        // one level-0 residual plane per resident CTA, or per pair in cluster mode (kept to short batches: 256 pairs)
         h->scratch_stride = h->lplane[0];
-        DVO_CUDA(h, cudaMalloc(&h->scratch, h->scratch_stride * sizeof(float) * (size_t)h->grid_max * kScratchSets));
+        h->scratch_planes = h->grid_max;
+        if (h->cfg.cluster_size > 1 && h->max_pairs <= kClusterTdistMaxPairs && h->max_pairs > h->scratch_planes)
+            h->scratch_planes = h->max_pairs;
+        DVO_CUDA(h, cudaMalloc(&h->scratch, h->scratch_stride * sizeof(float) * (size_t)h->scratch_planes * kScratchSets));
     }
     DVO_CUDA(h, cudaMalloc(&h->qt_init, sizeof(float) * 7 * h->max_pairs));
     DVO_CUDA(h, cudaMalloc(&h->qt_last, sizeof(float) * 7 * h->max_pairs));
@@ -552,12 +562,13 @@ extern "C" int dvo_estimate(dvo_handle* h, int prev_base, int cur_base, int n_pa
     p.out_qt = out_qt_dev;
     p.stats = stats_dev;
     p.queue = h->queue + h->queue_next;
-    if (h->scratch) p.scratch = h->scratch + (size_t)(h->queue_next % kScratchSets) * h->scratch_stride * (size_t)h->grid_max;
+    if (h->scratch) p.scratch = h->scratch + (size_t)(h->queue_next % kScratchSets) * h->scratch_stride * (size_t)h->scratch_planes;
     h->queue_next = (h->queue_next + 1) % (kQueueSlots / kScratchSets * kScratchSets);
     DVO_CUDA(h, cudaMemsetAsync(p.queue, 0, sizeof(int), st));
     const int grid = n_pairs < h->grid_max ? n_pairs : h->grid_max;
     align_fn fn = get_align(h);
     align_fn cfn = (h->cfg.cluster_size > 1 && !h->cfg.use_depth_residual) ? get_cluster(h) : nullptr;
+    if (cfn && h->cfg.weights == DVO_W_TDIST_REF && n_pairs > h->scratch_planes) cfn = nullptr;  // no plane per pair
     DVO_CUDA(h, cudaEventRecord(h->ev0, st));
     void* args[] = {&p};
     if (cfn) {

@@ -563,6 +563,39 @@ def test_cluster_mode_matches_reference_and_single_cta(dvo_mod, testdata_frames,
     np.testing.assert_array_equal(s1["n_valid"][0][:4], s0["n_valid"][0][:4])
 
 
+@pytest.mark.parametrize("cluster", [2, 8])
+def test_cluster_mode_tdist_matches_reference_and_single_cta(dvo_mod, testdata_frames, golden_dir, cluster):
+    """The reference's t-distribution weights in cluster mode: the lambda fixed point is reduced across the cluster
+    through distributed shared memory and the residual plane is shared by the cluster's CTAs.  Same pose as the REAL
+    reference and as the one-CTA kernel, deterministic from run to run; a short batch (one plane per pair) too."""
+    m = dvo_mod
+    f = testdata_frames
+    cam = m.RGBDCameraModel(_Km(f["K"]), f["depth_scale"])
+    rep = lambda k, n=2: (np.stack(f["bgr"][k:k + n]), np.stack([d.copy() for d in f["depth"][k:k + n]]))  # noqa: E731
+    g = np.load(golden_dir / "pose_testdata_1_2_tdist.npz")
+    single = m.SequenceAligner(cam, 480, 640, 4, max_frames=4, use_weighter=True)
+    clus = m.SequenceAligner(cam, 480, 640, 4, max_frames=4, use_weighter=True, cluster_size=cluster)
+    q0, s0 = single.align(*rep(0, 4))
+    q1, s1 = clus.align(*rep(0, 4))
+    q2, s2 = clus.align(*rep(0, 4))
+    np.testing.assert_array_equal(q1, q2)                      # run-to-run deterministic
+    print("cluster t-dist |dq|", np.abs(q1 - q0).max(), s1["iters"][:, :4].tolist(), s0["iters"][:, :4].tolist())
+    assert np.abs(q1 - q0).max() < 2e-5
+    assert np.abs(q1[0, :4] - g["q"].reshape(4)).max() < POSE_TOL and np.abs(q1[0, 4:] - g["t"].reshape(3)).max() < POSE_TOL
+    np.testing.assert_array_equal(s1["n_valid"][:, :4], s0["n_valid"][:, :4])
+    for extra in ({"tdist_mean": True}, {"oob_mode": "strict"}, {"approximate_image2_gradient": True}):
+        kw = dict(use_weighter=True)
+        if extra.get("tdist_mean"):
+            kw = dict(weights="tdist_mean")
+        else:
+            kw.update(extra)
+        a = m.SequenceAligner(cam, 480, 640, 4, max_frames=2, **kw)
+        b = m.SequenceAligner(cam, 480, 640, 4, max_frames=2, cluster_size=cluster, **kw)
+        qa, _ = a.align(*rep(2))
+        qb, _ = b.align(*rep(2))
+        assert np.abs(qa - qb).max() < 2e-5, extra
+
+
 def test_cluster_mode_odd_sizes_huber_and_approximate(dvo_mod, golden_dir):
     m = dvo_mod
     rep = lambda a: np.ascontiguousarray(np.repeat(a[..., None], 3, axis=-1))  # noqa: E731
@@ -583,7 +616,7 @@ def test_cluster_mode_odd_sizes_huber_and_approximate(dvo_mod, golden_dir):
             qa, _ = a.align(*args)
             qb, _ = b.align(*args)
             assert np.abs(qa - qb).max() < 2e-5, kw
-    # t-distribution weights ignore the cluster request and still match the reference
+    # t-distribution weights in cluster mode (one residual plane per cluster) still match the reference
     g = np.load(golden_dir / "pose_syn160.npz")
     cam = m.RGBDCameraModel(_Km(tuple(float(v) for v in g["K"])), float(g["depth_scale"]))
     al = m.PairBatchAligner(cam, 120, 160, 3, max_pairs=1, use_weighter=True, cluster_size=8)
