@@ -294,12 +294,12 @@ def gpu_arm(args):
         hbuf.copy_(x)
     torch.cuda.synchronize(dev)
     for _ in range(max(1, min(args.warmup, 2))):
-        al.align(*hb)
+        al.align(*hb, chunk_pairs=args.chunk_pairs)
     barrier()
     t0 = time.perf_counter()
     e2e_steps = args.e2e_steps or args.steps
     for _ in range(e2e_steps):
-        qt_e, st_e = al.align(*hb)       # H2D of all four buffers, kernels, D2H of poses + stats, stream sync
+        qt_e, st_e = al.align(*hb, chunk_pairs=args.chunk_pairs)       # H2D of all four buffers, kernels, D2H of poses + stats, stream sync
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -405,6 +405,7 @@ def main():
     ap.add_argument("--prefetch-rows", type=int, default=0)
     ap.add_argument("--approximate-gradient", action="store_true",
                     help="the reference's approximate_image2_gradient=True mode (not the headline configuration)")
+    ap.add_argument("--chunk-pairs", type=int, default=256, help="end-to-end leg: pairs per upload/compute chunk")
     ap.add_argument("--depth-residual", action="store_true",
                     help="photometric + depth residual (extension, BASELINE.json configs[4]; not the headline configuration)")
     args = ap.parse_args()

@@ -366,20 +366,18 @@ extern "C" long long dvo_launch_count(const dvo_handle* h) { return h ? h->launc
 // ---- pyramids ----------------------------------------------------------------------------------
 static int build_levels(dvo_handle* h, int frame_base, int n_frames, int with_gradients, cudaStream_t st) {
     for (int l = 1; l < h->levels; ++l) {
-        dim3 grid(((h->lw[l] + 3) / 4 + 127) / 128, h->lh[l], n_frames);
-        median3_down_kernel<uint8_t><<<grid, 128, 0, st>>>(
+        const int groups = (h->lw[l] + 3) / 4 * h->lh[l];
+        dim3 grid((groups + 127) / 128, n_frames);
+        median3_down_pair_kernel<<<grid, 128, 0, st>>>(
             h->gray[l - 1] + (size_t)frame_base * h->lplane[l - 1], h->gray[l] + (size_t)frame_base * h->lplane[l],
-            h->lw[l - 1], h->lh[l - 1], h->lpitch[l - 1], h->lplane[l - 1], h->lw[l], h->lh[l], h->lpitch[l],
-            h->lplane[l]);
-        median3_down_kernel<uint16_t><<<grid, 128, 0, st>>>(
             h->depth[l - 1] + (size_t)frame_base * h->lplane[l - 1], h->depth[l] + (size_t)frame_base * h->lplane[l],
             h->lw[l - 1], h->lh[l - 1], h->lpitch[l - 1], h->lplane[l - 1], h->lw[l], h->lh[l], h->lpitch[l],
             h->lplane[l]);
-        h->launches += 2;
+        h->launches += 1;
     }
     if (with_gradients) {
         for (int l = 0; l < h->levels; ++l) {
-            dim3 grid(((h->lw[l] + 3) / 4 + 127) / 128, h->lh[l], n_frames);
+            dim3 grid(((h->lw[l] + 3) / 4 * h->lh[l] + 127) / 128, n_frames);
             sobel3_kernel<<<grid, 128, 0, st>>>(h->gray[l] + (size_t)frame_base * h->lplane[l],
                                                 h->rec[l] + (size_t)frame_base * h->lplane[l], h->lw[l], h->lh[l],
                                                 h->lpitch[l], h->lplane[l]);

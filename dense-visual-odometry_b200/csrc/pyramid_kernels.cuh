@@ -2,7 +2,7 @@
 //
 //   gray_clamp_kernel     BGR u8 -> gray u8 (OpenCV fixed point) + far-depth -> 0, both into level 0
 //                         (reference: core/base_dense_visual_odometry.py:58-59)
-//   median3_down_kernel   3x3 median, replicated border, keep even rows/cols
+//   median3_down_pair_kernel  3x3 median, replicated border, keep even rows/cols (gray and depth level in one launch)
 //                         (reference: utils/image_pyramid.py:19-21, cv2.medianBlur(.,3)[::2, ::2])
 //   sobel3_kernel         3x3 Sobel dx/dy, gain 8, replicated border -> packed 8-byte records {gx, gy, I}
 //                         (reference: utils/jacobian.py:70-71; layout: rec_pack in align_kernel.cuh); the
@@ -139,35 +139,52 @@ __device__ __forceinline__ void load_row9(const T* __restrict__ row, int k, int 
     }
 }
 
-// One thread per FOUR output pixels of a row: only the kept (even, even) medians are computed.
-template <typename T>
-__global__ void __launch_bounds__(128) median3_down_kernel(const T* __restrict__ src, T* __restrict__ dst, int sw,
-                                                           int sh, int spitch, size_t splane, int dw, int dh,
-                                                           int dpitch, size_t dplane) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const int oy = blockIdx.y;
-    const int frame = blockIdx.z;
+// One thread per FOUR output pixels of a row; only the kept (even, even) medians are computed.
+// Both planes of a frame in one launch: the gray (u8) and depth (u16) levels share their geometry, so one thread
+// produces four gray and four depth outputs, with all six source-row loads issued before the first median; threads
+// are numbered linearly over (output row, 4-pixel group) so that the narrow coarse levels still fill their blocks
+// (one block per row left 37-84 % of the threads idle there).
+__global__ void __launch_bounds__(128) median3_down_pair_kernel(const uint8_t* __restrict__ src8, uint8_t* __restrict__ dst8,
+                                                                const uint16_t* __restrict__ src16,
+                                                                uint16_t* __restrict__ dst16, int sw, int sh, int spitch,
+                                                                size_t splane, int dw, int dh, int dpitch, size_t dplane) {
+    const int kpr = (dw + 3) >> 2;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= kpr * dh) return;
+    const int oy = idx / kpr;
+    const int k = idx - oy * kpr;
+    const int frame = blockIdx.y;
     const int ox = 4 * k;
-    if (ox >= dw) return;
     const int cy = oy * 2;
-    const T* s = src + (size_t)frame * splane;
-    int r0[9], r1[9], r2[9];
-    load_row9(s + (size_t)max(cy - 1, 0) * spitch, k, sw, r0);
-    load_row9(s + (size_t)cy * spitch, k, sw, r1);
-    load_row9(s + (size_t)min(cy + 1, sh - 1) * spitch, k, sw, r2);
-    int m[4];
+    const size_t ra = (size_t)max(cy - 1, 0) * spitch, rb = (size_t)cy * spitch, rc = (size_t)min(cy + 1, sh - 1) * spitch;
+    const uint8_t* s8 = src8 + (size_t)frame * splane;
+    const uint16_t* s16 = src16 + (size_t)frame * splane;
+    int a0[9], a1[9], a2[9], b0[9], b1[9], b2[9];
+    load_row9(s8 + ra, k, sw, a0);
+    load_row9(s8 + rb, k, sw, a1);
+    load_row9(s8 + rc, k, sw, a2);
+    load_row9(s16 + ra, k, sw, b0);
+    load_row9(s16 + rb, k, sw, b1);
+    load_row9(s16 + rc, k, sw, b2);
+    int m[4], n[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-        m[j] = median9<int>(r0[2 * j], r0[2 * j + 1], r0[2 * j + 2], r1[2 * j], r1[2 * j + 1], r1[2 * j + 2],
-                            r2[2 * j], r2[2 * j + 1], r2[2 * j + 2]);
-    T* d = dst + (size_t)frame * dplane + (size_t)oy * dpitch + ox;
+    for (int j = 0; j < 4; ++j) {
+        m[j] = median9<int>(a0[2 * j], a0[2 * j + 1], a0[2 * j + 2], a1[2 * j], a1[2 * j + 1], a1[2 * j + 2],
+                            a2[2 * j], a2[2 * j + 1], a2[2 * j + 2]);
+        n[j] = median9<int>(b0[2 * j], b0[2 * j + 1], b0[2 * j + 2], b1[2 * j], b1[2 * j + 1], b1[2 * j + 2],
+                            b2[2 * j], b2[2 * j + 1], b2[2 * j + 2]);
+    }
+    const size_t o = (size_t)frame * dplane + (size_t)oy * dpitch + ox;
     if (ox + 3 < dw) {
-        if (sizeof(T) == 1)
-            *reinterpret_cast<uint32_t*>(d) = (uint32_t)m[0] | ((uint32_t)m[1] << 8) | ((uint32_t)m[2] << 16) | ((uint32_t)m[3] << 24);
-        else
-            *reinterpret_cast<uint2*>(d) = make_uint2((uint32_t)m[0] | ((uint32_t)m[1] << 16), (uint32_t)m[2] | ((uint32_t)m[3] << 16));
+        *reinterpret_cast<uint32_t*>(dst8 + o) =
+            (uint32_t)m[0] | ((uint32_t)m[1] << 8) | ((uint32_t)m[2] << 16) | ((uint32_t)m[3] << 24);
+        *reinterpret_cast<uint2*>(dst16 + o) =
+            make_uint2((uint32_t)n[0] | ((uint32_t)n[1] << 16), (uint32_t)n[2] | ((uint32_t)n[3] << 16));
     } else {
-        for (int j = 0; j < 4 && ox + j < dw; ++j) d[j] = (T)m[j];   // padding columns stay zero
+        for (int j = 0; j < 4 && ox + j < dw; ++j) {   // padding columns stay zero
+            dst8[o + j] = (uint8_t)m[j];
+            dst16[o + j] = (uint16_t)n[j];
+        }
     }
 }
 
@@ -188,10 +205,13 @@ __device__ __forceinline__ void load_row6(const uint8_t* __restrict__ row, int x
 
 __global__ void __launch_bounds__(128) sobel3_kernel(const uint8_t* __restrict__ gray, uint2* __restrict__ rec,
                                                      int w, int h, int pitch, size_t plane) {
-    const int x0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
-    const int y = blockIdx.y;
-    const int frame = blockIdx.z;
-    if (x0 >= w) return;
+    // threads numbered linearly over (row, 4-pixel group): narrow levels still fill their blocks
+    const int gpr = (w + 3) >> 2;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= gpr * h) return;
+    const int y = idx / gpr;
+    const int x0 = 4 * (idx - y * gpr);
+    const int frame = blockIdx.y;
     const uint8_t* s = gray + (size_t)frame * plane;
     int a[6], b[6], c[6];
     load_row6(s + (size_t)max(y - 1, 0) * pitch, x0, w, a);
