@@ -207,15 +207,21 @@ def gpu_arm(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    local_cpus = []
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep the version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
+        if not args.no_numa_bind:
+            # one process per GPU: keep this rank's pinned staging memory (and its copies) on the GPU's own NUMA node
+            from dense_visual_odometry_b200.sharding import bind_to_gpu_local_cpus
+            local_cpus = bind_to_gpu_local_cpus(local_rank)
 
     import dense_visual_odometry_b200 as dvo
     from dense_visual_odometry_b200.synthetic import make_pairs_numpy, make_pairs_torch, TUM_FR1, TUM_DEPTH_SCALE
 
     B = args.pairs
-    n_cpu = min(args.cpu_pairs or min(host_cores(), 32), B) if rank == 0 else 0
+    # the CPU baseline is timed on rank 0 at N = 1 only
+    n_cpu = min(args.cpu_pairs or min(host_cores(), 32), B) if (rank == 0 and world == 1) else 0
     base = rank * B
     # pairs [0, n_cpu) of rank 0 are rendered with NumPy so the CPU baseline sees bit-identical inputs
     Km = np.array([[TUM_FR1[0], 0, TUM_FR1[2]], [0, TUM_FR1[1], TUM_FR1[3]], [0, 0, 1]], dtype=np.float32)
@@ -361,6 +367,7 @@ def gpu_arm(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "pairs_per_gpu": B, "global_pairs": world * B,
                        "levels": LEVELS, "weights": args.weights, "parallelism": f"pairs sharded over {world} GPU(s)",
+                       "host_cpu_binding": (f"rank 0 bound to {len(local_cpus)} GPU-local cores" if local_cpus else "none"),
                        "l2_policy": "inputs larger than L2 (%.2f GB of frames + %.2f GB of pyramids per GPU)" % (
                            2 * B * H * W * 5 / 1e9, 2 * B * 437760 * 11 / 1e9),
                        "threads_per_block": args.threads or 128},
@@ -429,6 +436,8 @@ def main():
     ap.add_argument("--prefetch-rows", type=int, default=0)
     ap.add_argument("--approximate-gradient", action="store_true",
                     help="the reference's approximate_image2_gradient=True mode (not the headline configuration)")
+    ap.add_argument("--no-numa-bind", action="store_true",
+                    help="N > 1: do not pin each rank to the CPU cores local to its GPU")
     ap.add_argument("--chunk-pairs", type=int, default=256, help="end-to-end leg: pairs per upload/compute chunk")
     ap.add_argument("--depth-residual", action="store_true",
                     help="photometric + depth residual (extension, BASELINE.json configs[4]; not the headline configuration)")

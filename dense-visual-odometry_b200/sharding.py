@@ -59,3 +59,30 @@ def chain_poses(relative_qt, initial=None):
         cur = cur * Se3.from_qt(row).inverse()
         out.append(cur.copy())
     return out
+
+
+def bind_to_gpu_local_cpus(device_index: int):
+    """Restricts this process to the CPU cores NVML reports as local to GPU `device_index` (same NUMA node / PCIe root),
+    so that the pinned staging buffers it allocates afterwards land in that node's memory.  With one process per GPU
+    on a multi-socket host this keeps every rank's host-to-device copies off the inter-socket link.  Returns the core
+    list, or [] if NVML or the affinity call is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid if not uuid.startswith("GPU-") else uuid).encode())
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        allowed = os.sched_getaffinity(0)
+        cpus = [w * 64 + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1 and (w * 64 + b) in allowed]
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return []
