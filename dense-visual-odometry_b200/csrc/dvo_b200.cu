@@ -574,7 +574,7 @@ extern "C" int dvo_estimate(dvo_handle* h, int prev_base, int cur_base, int n_pa
         if (C > 8) DVO_CUDA(h, cudaFuncSetAttribute((const void*)cfn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         cudaLaunchConfig_t lc = {};
         lc.gridDim = dim3((unsigned)n_pairs * (unsigned)C);
-        lc.blockDim = dim3(128);
+        lc.blockDim = dim3(kClusterThreads);
         lc.dynamicSmemBytes = 0;
         lc.stream = st;
         cudaLaunchAttribute at[1];

@@ -77,3 +77,36 @@ def test_test_format_loader(tmp_path, testdata_frames):
     np.testing.assert_array_equal(colors, f["bgr"][:3])      # PNG is lossless: the exact frames come back, BGR
     np.testing.assert_array_equal(depths, f["depth"][:3])
     assert D.read_frames(seq, bgr=False)[0][0, 0, 0, 0] == f["bgr"][0][0, 0, 2]
+
+
+def test_synthetic_sequence_is_consistent_and_deterministic():
+    """BASELINE.json configs[2] generator: the relative twists chain to the absolute poses the frames were rendered
+    from, frame 0 is the identity view, and the stream is reproducible."""
+    from dense_visual_odometry_b200.synthetic import make_sequence, make_sequence_motions, se3_exp
+    xi, R_abs, t_abs = make_sequence_motions(6, seed=5)
+    assert xi.shape == (5, 6) and R_abs.shape == (6, 3, 3) and t_abs.shape == (6, 3)
+    assert np.allclose(R_abs[0], np.eye(3)) and not t_abs[0].any()
+    R, t = np.eye(3), np.zeros(3)
+    for k in range(5):
+        Rk, tk = se3_exp(xi[k])
+        R, t = Rk @ R, Rk @ t + tk
+        assert np.allclose(R, R_abs[k + 1]) and np.allclose(t, t_abs[k + 1])
+    assert np.abs(xi[:, :3]).max() <= 0.02 and np.abs(xi[:, 3:]).max() <= 0.01
+    a = make_sequence(3, height=48, width=64)
+    b = make_sequence(3, height=48, width=64)
+    assert a["bgr"].shape == (3, 48, 64, 3) and a["depth"].shape == (3, 48, 64) and a["depth"].dtype == np.uint16
+    assert np.array_equal(a["bgr"], b["bgr"]) and np.array_equal(a["depth"], b["depth"])
+    assert (a["depth"] == 0).mean() > 0.02          # every frame has depth holes
+    assert not np.array_equal(a["bgr"][0], a["bgr"][1])
+
+
+def test_gpu_local_cpu_binding_is_harmless_without_nvml():
+    """The N > 1 host helper must never raise or shrink the affinity to nothing on a box without a GPU."""
+    import os
+    from dense_visual_odometry_b200.sharding import bind_to_gpu_local_cpus
+    before = os.sched_getaffinity(0)
+    cpus = bind_to_gpu_local_cpus(0)
+    after = os.sched_getaffinity(0)
+    assert isinstance(cpus, list)
+    assert after == before or (cpus and set(cpus) == after)
+    os.sched_setaffinity(0, before)
