@@ -499,9 +499,15 @@ static void fill_params(const dvo_handle* h, AlignParams& p) {
         g.strips = h->lpitch[l] / kTile;
         g.n_tiles = g.strips * h->lh[l];
         g.h_magic = (unsigned)((1ull << 32) / (unsigned)h->lh[l]) + 1u;
-        {   // chunks per strip = NW * k with about 60 rows per chunk (align_kernel.cuh, fused_pass)
+        {   // chunks per strip = NW * k with about 120 rows per chunk (align_kernel.cuh, fused_pass); measured per
+            // 2048 pairs: 30 / 60 / 120 / 240 rows -> 83.3 (60), 82.2 (120), 83.4 (240) ms
             const int nw = h->threads / 32;
-            int k = (h->lh[l] + nw * 30) / (nw * 60);
+            static const int target = [] {   // developer knob DVO_TUNE_CHUNK_ROWS (rows per chunk aimed at, default 120)
+                const char* e = getenv("DVO_TUNE_CHUNK_ROWS");
+                const int v = e ? atoi(e) : 0;
+                return (v >= 8 && v <= 2048) ? v : 120;
+            }();
+            int k = (h->lh[l] + nw * (target / 2)) / (nw * target);
             if (k < 1) k = 1;
             g.chunks_per_strip = nw * k;
             g.chunk_rows = (h->lh[l] + g.chunks_per_strip - 1) / g.chunks_per_strip;
