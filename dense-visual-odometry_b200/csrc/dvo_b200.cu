@@ -1,5 +1,6 @@
 // libdvo_b200.so — C ABI (include/dvo_b200.h) over the sm_100a kernels.
-// Build: nvcc -shared -Xcompiler -fPIC -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 (see __graft_entry__.build).
+// Build: every csrc/*.cu with nvcc -c -Xcompiler -fPIC -gencode arch=compute_100a,code=sm_100a -lineinfo -O3, linked with
+// nvcc -shared (see __graft_entry__.build, which compiles the translation units in parallel).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -12,6 +13,7 @@
 #include "../../include/dvo_b200.h"
 #include "align_kernel.cuh"
 #include "pyramid_kernels.cuh"
+#include "variants.cuh"
 
 using namespace dvo;
 
@@ -87,77 +89,22 @@ extern "C" void dvo_default_config(dvo_config* cfg) {
 extern "C" const char* dvo_last_error(const dvo_handle* h) { return h ? h->err.c_str() : kNullHandle; }
 
 // ---- kernel dispatch ---------------------------------------------------------------------------
-typedef void (*align_fn)(const AlignParams);
-
-template <int T, int B>
-static align_fn pick_align(int w, int oob, int grad, int depth) {
-    if (depth) {  // photometric + depth residual (extension): unweighted or fixed-threshold Huber photometric term
-#define DVO_PICKD(WM, OM) \
-    if (w == WM && oob == OM && grad == 0) return (align_fn)align_kernel<WM, OM, 0, T, B, 1>;
-#ifndef DVO_FAST_BUILD
-        DVO_PICKD(DVO_W_NONE, DVO_OOB_INCLUSIVE)
-        DVO_PICKD(DVO_W_NONE, DVO_OOB_STRICT)
-        DVO_PICKD(DVO_W_HUBER, DVO_OOB_INCLUSIVE)
-        DVO_PICKD(DVO_W_HUBER, DVO_OOB_STRICT)
-#endif
-#undef DVO_PICKD
-        return nullptr;
-    }
-#define DVO_PICK(WM, OM, GM) \
-    if (w == WM && oob == OM && grad == GM) return (align_fn)align_kernel<WM, OM, GM, T, B>;
-    DVO_PICK(DVO_W_NONE, DVO_OOB_INCLUSIVE, 0)
-#ifndef DVO_FAST_BUILD
-    DVO_PICK(DVO_W_NONE, DVO_OOB_STRICT, 0)
-    DVO_PICK(DVO_W_TDIST_REF, DVO_OOB_INCLUSIVE, 0)
-    DVO_PICK(DVO_W_TDIST_REF, DVO_OOB_STRICT, 0)
-    DVO_PICK(DVO_W_HUBER, DVO_OOB_INCLUSIVE, 0)
-    DVO_PICK(DVO_W_HUBER, DVO_OOB_STRICT, 0)
-    DVO_PICK(DVO_W_NONE, DVO_OOB_INCLUSIVE, 1)
-    DVO_PICK(DVO_W_NONE, DVO_OOB_STRICT, 1)
-    DVO_PICK(DVO_W_TDIST_REF, DVO_OOB_INCLUSIVE, 1)
-    DVO_PICK(DVO_W_TDIST_REF, DVO_OOB_STRICT, 1)
-    DVO_PICK(DVO_W_HUBER, DVO_OOB_INCLUSIVE, 1)
-    DVO_PICK(DVO_W_HUBER, DVO_OOB_STRICT, 1)
-    DVO_PICK(DVO_W_HUBER_MAD, DVO_OOB_INCLUSIVE, 0)
-    DVO_PICK(DVO_W_HUBER_MAD, DVO_OOB_STRICT, 0)
-    DVO_PICK(DVO_W_HUBER_MAD, DVO_OOB_INCLUSIVE, 1)
-    DVO_PICK(DVO_W_HUBER_MAD, DVO_OOB_STRICT, 1)
-#endif
-#undef DVO_PICK
-    return nullptr;
-}
-
+// The alignment-kernel instantiations live in variants_*.cu (compiled in parallel); see variants.cuh.
 // Launch shapes: 128 threads x 2 CTAs per SM (default: one CTA's reduction / solve overlaps the other's streaming)
 // or 256 threads x 1 CTA per SM (lower latency for a single pair).  Both run 8 warps per SM at 255 registers;
 // shapes with more warps per SM spill inside the pipelined loop and measured slower (profiles/r1/SUMMARY.md).
 static align_fn get_align(const dvo_handle* h) {
     const int w = h->cfg.weights, o = h->cfg.oob_mode, gm = h->cfg.approximate_image2_gradient ? 1 : 0;
     const int dz = h->cfg.use_depth_residual ? 1 : 0;
-    if (h->threads == 256) return pick_align<256, 1>(w, o, gm, dz);
-    return pick_align<128, 2>(w, o, gm, dz);
+    if (gm && dz) return nullptr;
+    if (h->threads == 256) return gm ? pick_align_256_g1(w, o) : pick_align_256_g0(w, o, dz);
+    return gm ? pick_align_128_g1(w, o) : pick_align_128_g0(w, o, dz);
 }
 
-// Cluster-mode kernel (one thread-block cluster per pair); not built for the t-distribution weights.
+// Cluster-mode kernel (one thread-block cluster per pair); not built for the Huber/MAD weights.
 static align_fn get_cluster(const dvo_handle* h) {
-    const int w = h->cfg.weights, o = h->cfg.oob_mode, gm = h->cfg.approximate_image2_gradient ? 1 : 0;
-#define DVO_PICKC(WM, OM, GM) \
-    if (w == WM && o == OM && gm == GM) return (align_fn)align_cluster_kernel<WM, OM, GM>;
-    DVO_PICKC(DVO_W_NONE, DVO_OOB_INCLUSIVE, 0)
-#ifndef DVO_FAST_BUILD
-    DVO_PICKC(DVO_W_NONE, DVO_OOB_STRICT, 0)
-    DVO_PICKC(DVO_W_HUBER, DVO_OOB_INCLUSIVE, 0)
-    DVO_PICKC(DVO_W_HUBER, DVO_OOB_STRICT, 0)
-    DVO_PICKC(DVO_W_NONE, DVO_OOB_INCLUSIVE, 1)
-    DVO_PICKC(DVO_W_NONE, DVO_OOB_STRICT, 1)
-    DVO_PICKC(DVO_W_HUBER, DVO_OOB_INCLUSIVE, 1)
-    DVO_PICKC(DVO_W_HUBER, DVO_OOB_STRICT, 1)
-    DVO_PICKC(DVO_W_TDIST_REF, DVO_OOB_INCLUSIVE, 0)
-    DVO_PICKC(DVO_W_TDIST_REF, DVO_OOB_STRICT, 0)
-    DVO_PICKC(DVO_W_TDIST_REF, DVO_OOB_INCLUSIVE, 1)
-    DVO_PICKC(DVO_W_TDIST_REF, DVO_OOB_STRICT, 1)
-#endif
-#undef DVO_PICKC
-    return nullptr;
+    const int w = h->cfg.weights, o = h->cfg.oob_mode;
+    return h->cfg.approximate_image2_gradient ? pick_cluster_g1(w, o) : pick_cluster_g0(w, o);
 }
 
 typedef void (*dump_fn)(const AlignParams, int, int, int, const float*, float, float*, float*, uint8_t*, uint8_t*,

@@ -1,0 +1,76 @@
+// Kernel dispatch tables, split over several translation units so that the ~60 template instantiations of the
+// alignment kernel compile in parallel (__graft_entry__.build): each variants_*.cu instantiates one slice and
+// exports one pick function; dvo_b200.cu only calls them.
+#pragma once
+#include "align_kernel.cuh"
+
+namespace dvo {
+
+typedef void (*align_fn)(const AlignParams);
+
+// weights x oob_mode for one launch shape (T threads, B CTAs per SM) and one gradient mode G; depth != 0 selects the
+// photometric + depth residual variants (G = 0, unweighted or fixed-threshold Huber only).  nullptr = not built.
+template <int T, int B, int G>
+static align_fn pick_variants(int w, int oob, int depth) {
+#ifdef DVO_FAST_BUILD   // developer build: the headline variant only
+    if (T == 128 && G == 0 && !depth && w == DVO_W_NONE && oob == DVO_OOB_INCLUSIVE)
+        return (align_fn)align_kernel<DVO_W_NONE, DVO_OOB_INCLUSIVE, G, T, B>;
+    return nullptr;
+#else
+    if (depth) {
+        if constexpr (G == 0) {
+#define DVO_PICKD(WM, OM) \
+    if (w == WM && oob == OM) return (align_fn)align_kernel<WM, OM, 0, T, B, 1>;
+            DVO_PICKD(DVO_W_NONE, DVO_OOB_INCLUSIVE)
+            DVO_PICKD(DVO_W_NONE, DVO_OOB_STRICT)
+            DVO_PICKD(DVO_W_HUBER, DVO_OOB_INCLUSIVE)
+            DVO_PICKD(DVO_W_HUBER, DVO_OOB_STRICT)
+#undef DVO_PICKD
+        }
+        return nullptr;
+    }
+#define DVO_PICK(WM, OM) \
+    if (w == WM && oob == OM) return (align_fn)align_kernel<WM, OM, G, T, B>;
+    DVO_PICK(DVO_W_NONE, DVO_OOB_INCLUSIVE)
+    DVO_PICK(DVO_W_NONE, DVO_OOB_STRICT)
+    DVO_PICK(DVO_W_TDIST_REF, DVO_OOB_INCLUSIVE)
+    DVO_PICK(DVO_W_TDIST_REF, DVO_OOB_STRICT)
+    DVO_PICK(DVO_W_HUBER, DVO_OOB_INCLUSIVE)
+    DVO_PICK(DVO_W_HUBER, DVO_OOB_STRICT)
+    DVO_PICK(DVO_W_HUBER_MAD, DVO_OOB_INCLUSIVE)
+    DVO_PICK(DVO_W_HUBER_MAD, DVO_OOB_STRICT)
+#undef DVO_PICK
+    return nullptr;
+#endif
+}
+
+// Cluster-mode kernels (one thread-block cluster per pair) for one gradient mode; not built for Huber/MAD.
+template <int G>
+static align_fn pick_cluster_variants(int w, int oob) {
+#ifdef DVO_FAST_BUILD
+    if (G == 0 && w == DVO_W_NONE && oob == DVO_OOB_INCLUSIVE)
+        return (align_fn)align_cluster_kernel<DVO_W_NONE, DVO_OOB_INCLUSIVE, G>;
+    return nullptr;
+#else
+#define DVO_PICKC(WM, OM) \
+    if (w == WM && oob == OM) return (align_fn)align_cluster_kernel<WM, OM, G>;
+    DVO_PICKC(DVO_W_NONE, DVO_OOB_INCLUSIVE)
+    DVO_PICKC(DVO_W_NONE, DVO_OOB_STRICT)
+    DVO_PICKC(DVO_W_HUBER, DVO_OOB_INCLUSIVE)
+    DVO_PICKC(DVO_W_HUBER, DVO_OOB_STRICT)
+    DVO_PICKC(DVO_W_TDIST_REF, DVO_OOB_INCLUSIVE)
+    DVO_PICKC(DVO_W_TDIST_REF, DVO_OOB_STRICT)
+#undef DVO_PICKC
+    return nullptr;
+#endif
+}
+
+// one definition per variants_*.cu
+align_fn pick_align_128_g0(int w, int oob, int depth);
+align_fn pick_align_128_g1(int w, int oob);
+align_fn pick_align_256_g0(int w, int oob, int depth);
+align_fn pick_align_256_g1(int w, int oob);
+align_fn pick_cluster_g0(int w, int oob);
+align_fn pick_cluster_g1(int w, int oob);
+
+}  // namespace dvo
