@@ -13,7 +13,7 @@ typedef void (*align_fn)(const AlignParams);
 template <int T, int B, int G>
 static align_fn pick_variants(int w, int oob, int depth) {
 #ifdef DVO_FAST_BUILD   // developer build: the headline variant only
-    if (T == 128 && G == 0 && !depth && w == DVO_W_NONE && oob == DVO_OOB_INCLUSIVE)
+    if (G == 0 && !depth && w == DVO_W_NONE && oob == DVO_OOB_INCLUSIVE)
         return (align_fn)align_kernel<DVO_W_NONE, DVO_OOB_INCLUSIVE, G, T, B>;
     return nullptr;
 #else
