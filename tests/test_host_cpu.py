@@ -109,3 +109,38 @@ def test_product_does_not_import_oracle():
     for p in pkg.glob("*.py"):
         src = p.read_text()
         assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), p
+
+
+def test_ctypes_structs_match_the_c_header(built, tmp_path):
+    """The ctypes mirrors of dvo_config / dvo_pair_stats have the size and field offsets a C compiler gives the
+    structs of include/dvo_b200.h (the header is plain C: it must compile with gcc, no CUDA)."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from dense_visual_odometry_b200 import _cabi
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    fields = {"dvo_config": [f[0] for f in _cabi.dvo_config._fields_],
+              "dvo_pair_stats": [f[0] for f in _cabi.dvo_pair_stats._fields_]}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT / "include" / "dvo_b200.h"}"', 'int main(void) {']
+    for s, names in fields.items():
+        lines.append(f'printf("{s} %zu\\n", sizeof({s}));')
+        for n in names:
+            lines.append(f'printf("{s}.{n} %zu\\n", offsetof({s}, {n}));')
+    lines += ['printf("DVO_MAX_LEVELS %d\\n", DVO_MAX_LEVELS);', 'printf("DVO_ACC_TERMS %d\\n", DVO_ACC_TERMS);',
+              'printf("W %d %d %d %d\\n", DVO_W_NONE, DVO_W_TDIST_REF, DVO_W_HUBER, DVO_W_HUBER_MAD);',
+              'printf("OOB %d %d\\n", DVO_OOB_INCLUSIVE, DVO_OOB_STRICT);', 'return 0; }']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-o", str(exe), str(src)], check=True)
+    out = dict(l.split(" ", 1) for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for s, names in fields.items():
+        cls = getattr(_cabi, s)
+        assert int(out[s]) == C.sizeof(cls), s
+        for n in names:
+            assert int(out[f"{s}.{n}"]) == getattr(cls, n).offset, f"{s}.{n}"
+    assert int(out["DVO_MAX_LEVELS"]) == _cabi.DVO_MAX_LEVELS and int(out["DVO_ACC_TERMS"]) == _cabi.DVO_ACC_TERMS
+    assert out["W"].split() == [str(v) for v in (_cabi.W_NONE, _cabi.W_TDIST_REF, _cabi.W_HUBER, _cabi.W_HUBER_MAD)]
+    assert out["OOB"].split() == [str(_cabi.OOB_INCLUSIVE), str(_cabi.OOB_STRICT)]
