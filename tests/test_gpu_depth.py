@@ -27,7 +27,7 @@ def dvo_mod():
     return m
 
 
-def _dense(vals, valid_n, mask, width):
+def _dense(vals, valid_n, mask):
     """(Nz, ...) values over valid depth pixels -> dense [H,W,...] with NaN / 0 elsewhere."""
     h, w = mask.shape
     full_valid = np.zeros(h * w, bool)
@@ -40,8 +40,8 @@ def _dense(vals, valid_n, mask, width):
 
 def _compare_depth_level(est, ld, pose, lv, oob, lam, report):
     rz, Jz, vz = O.depth_residuals_and_jacobian(ld, pose.exp(), oob)
-    rd, vd = _dense(rz.astype(np.float64), vz, ld.mask, ld.mask.shape[1])
-    Jd, _ = _dense(Jz.astype(np.float64), vz, ld.mask, ld.mask.shape[1])
+    rd, vd = _dense(rz.astype(np.float64), vz, ld.mask)
+    Jd, _ = _dense(Jz.astype(np.float64), vz, ld.mask)
     gr, gJ, gv, acc = est.depth_residuals_dense(pose, lv, est._hook_slots[0], est._hook_slots[1])
     n_mis = int((gv != vd).sum())
     report[f"L{lv}_valid_mismatch"] = n_mis
