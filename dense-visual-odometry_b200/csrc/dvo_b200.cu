@@ -217,9 +217,10 @@ static int create_impl(dvo_handle* h) {
     h->grid_max = h->sm_count * h->blocks_per_sm;
     DVO_CUDA(h, cudaMalloc(&h->queue, sizeof(int) * kQueueSlots));
     if (h->cfg.weights == DVO_W_TDIST_REF) {
-        // one level-0 residual plane per resident CTA, or per pair in cluster mode (kept to short batches: 256 pairs)
+        // one level-0 residual plane per CTA of the persistent grid (at most one CTA per pair, so never more than
+        // max_pairs), or per pair in cluster mode (kept to short batches: 256 pairs)
         h->scratch_stride = h->lplane[0];
-        h->scratch_planes = h->grid_max;
+        h->scratch_planes = h->grid_max < h->max_pairs ? h->grid_max : h->max_pairs;
         if (h->cfg.cluster_size > 1 && h->max_pairs <= kClusterTdistMaxPairs && h->max_pairs > h->scratch_planes)
             h->scratch_planes = h->max_pairs;
         DVO_CUDA(h, cudaMalloc(&h->scratch, h->scratch_stride * sizeof(float) * (size_t)h->scratch_planes * kScratchSets));
@@ -501,6 +502,7 @@ extern "C" int dvo_estimate(dvo_handle* h, int prev_base, int cur_base, int n_pa
     if (n_pairs < 1 || prev_base < 0 || cur_base < 0 || prev_base + n_pairs > h->max_frames ||
         cur_base + n_pairs > h->max_frames)
         return fail(h, DVO_ERR_RANGE, "pair range exceeds the frame slots");
+    if (n_pairs > h->max_pairs) return fail(h, DVO_ERR_RANGE, "n_pairs exceeds max_pairs");
     DVO_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     AlignParams p;
