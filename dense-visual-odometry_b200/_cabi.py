@@ -3,6 +3,7 @@ or a call fails, this raises."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 DVO_MAX_LEVELS = 8
@@ -10,7 +11,8 @@ DVO_ACC_TERMS = 29
 W_NONE, W_TDIST_REF, W_HUBER, W_HUBER_MAD = 0, 1, 2, 3
 OOB_INCLUSIVE, OOB_STRICT = 0, 1
 
-LIB_PATH = Path(__file__).resolve().parent / "libdvo_b200.so"
+# developer knob: DVO_B200_LIB points the binding at another build of the same C ABI (kernel experiments)
+LIB_PATH = Path(os.environ.get("DVO_B200_LIB") or (Path(__file__).resolve().parent / "libdvo_b200.so"))
 
 
 class DvoError(RuntimeError):

@@ -29,12 +29,10 @@ struct dvo_handle {
     uint8_t* gray[DVO_MAX_LEVELS]{};
     uint16_t* depth[DVO_MAX_LEVELS]{};
     uint2* rec[DVO_MAX_LEVELS]{};
+    float* prec[DVO_MAX_LEVELS]{};   // previous-frame planes: z and -(0.5 + I/512), 2 floats per pixel (align_kernel.cuh, prec_index)
     float k4[DVO_MAX_LEVELS][4]{}, kinv4[DVO_MAX_LEVELS][4]{};
     int* queue = nullptr;   // kQueueSlots pair counters; concurrent dvo_estimate calls (different streams) rotate through them
     int queue_next = 0;
-    float* scratch = nullptr;
-    size_t scratch_stride = 0;
-    int scratch_planes = 0;
     int sm_count = 0, threads = 256, blocks_per_sm = 2, grid_max = 0;
     uint8_t* stage_bgr = nullptr;
     uint16_t* stage_depth = nullptr;
@@ -43,15 +41,14 @@ struct dvo_handle {
     float* qt_out = nullptr;
     float* qt_one = nullptr;  // 7 + 12 floats for dvo_residuals_jacobian
     dvo_pair_stats* stats = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool ev_valid = false;
+    cudaEvent_t ev0[8]{}, ev1[8]{};   // event pairs of the last launches (ring): calls in flight on different streams
+    int ev_last = -1;                 // never share a pair; dvo_last_estimate_ms reads the most recent one
     long long launches = 0;
     std::string err;
 };
 
 static const int kQueueSlots = 256;
-static const int kClusterTdistMaxPairs = 256;  // cluster mode + t-distribution: one residual plane per pair
-static const int kScratchSets = 3;  // t-distribution residual planes for up to 3 estimate launches in flight
+static const int kMaxPrefetchRows = 32;  // upper bound of dvo_config.reserved[0]; the plane slack is derived from it
 static const char* kNullHandle = "null handle";
 
 #define DVO_CUDA(h, call)                                                                             \
@@ -138,9 +135,9 @@ extern "C" int dvo_destroy(dvo_handle* h) {
         cudaFree(h->gray[l]);
         cudaFree(h->depth[l]);
         cudaFree(h->rec[l]);
+        cudaFree(h->prec[l]);
     }
     cudaFree(h->queue);
-    cudaFree(h->scratch);
     cudaFree(h->stage_bgr);
     cudaFree(h->stage_depth);
     cudaFree(h->qt_init);
@@ -148,8 +145,10 @@ extern "C" int dvo_destroy(dvo_handle* h) {
     cudaFree(h->qt_out);
     cudaFree(h->qt_one);
     cudaFree(h->stats);
-    if (h->ev0) cudaEventDestroy(h->ev0);
-    if (h->ev1) cudaEventDestroy(h->ev1);
+    for (int i = 0; i < 8; ++i) {
+        if (h->ev0[i]) cudaEventDestroy(h->ev0[i]);
+        if (h->ev1[i]) cudaEventDestroy(h->ev1[i]);
+    }
     delete h;
     return DVO_OK;
 }
@@ -159,6 +158,10 @@ static int create_impl(dvo_handle* h) {
     cudaDeviceProp prop;
     DVO_CUDA(h, cudaGetDeviceProperties(&prop, h->device));
     h->sm_count = prop.multiProcessorCount;
+    if (h->cfg.reserved[0] > kMaxPrefetchRows) {   // the kernels read that many rows ahead; the plane slack is sized for it
+        h->err = "reserved[0] (L1 prefetch distance in rows) must be <= 32";
+        return DVO_ERR_INVALID;
+    }
     int w = h->W, hh = h->H;
     for (int l = 0; l < h->levels; ++l) {
         h->lw[l] = w;
@@ -171,16 +174,24 @@ static int create_impl(dvo_handle* h) {
             return DVO_ERR_INVALID;
         }
         const size_t n = h->lplane[l] * h->max_frames;
-        // the unclamped +1 taps of the last row of the last frame read up to pitch + 1 records past the end
-        const size_t n_rec = n + 34 * (size_t)h->lpitch[l];
-        // the align kernel prefetches previous-frame samples up to two tiles past a warp's range
-        const size_t n_raw = n + 35 * (size_t)h->lpitch[l];
+        // Reads past the end of the last frame slot (align_kernel.cuh, fused_pass / depth_pass), in rows of this level:
+        //   tap records / current depth: tap coordinates are validated (inside the plane, or (0,0)), the unclamped
+        //     (x0 + 1, y0 + 1) tap reads at most pitch + 1 elements past the plane, and the L1 touches run up to
+        //     kMaxPrefetchRows + 1 rows ahead of a tap: kMaxPrefetchRows + 2 rows + 1 element.
+        //   previous-frame records: the software pipeline loads 2 rows past a chunk's last row and touches up to
+        //     kMaxPrefetchRows rows (+ 128 elements of lane spread) ahead of that: kMaxPrefetchRows + 3 rows.
+        // One row more than needed is allocated for each.
+        const size_t n_rec = n + (size_t)(kMaxPrefetchRows + 3) * (size_t)h->lpitch[l];
+        const size_t n_raw = n + (size_t)(kMaxPrefetchRows + 4) * (size_t)h->lpitch[l];
         DVO_CUDA(h, cudaMalloc(&h->gray[l], n_raw));
         DVO_CUDA(h, cudaMalloc(&h->depth[l], n_raw * sizeof(uint16_t)));
         DVO_CUDA(h, cudaMalloc(&h->rec[l], n_rec * sizeof(uint2)));
         DVO_CUDA(h, cudaMemset(h->gray[l], 0, n_raw));
         DVO_CUDA(h, cudaMemset(h->depth[l], 0, n_raw * sizeof(uint16_t)));
         DVO_CUDA(h, cudaMemset(h->rec[l], 0, n_rec * sizeof(uint2)));
+        DVO_CUDA(h, cudaMalloc(&h->prec[l], 2 * n_raw * sizeof(float)));
+        prec_fill_kernel<<<h->sm_count * 8, 256>>>(h->prec[l], 2 * n_raw);   // "no depth" everywhere, padding keeps it
+        DVO_CUDA(h, cudaGetLastError());
         {   // strip = umulhi(t, floor(2^32/h)+1) must be exact for every tile index of the plane
             const unsigned magic = (unsigned)((1ull << 32) / (unsigned)hh) + 1u;
             const int strips = h->lpitch[l] / kTile;
@@ -195,8 +206,8 @@ static int create_impl(dvo_handle* h) {
         w = (w + 1) / 2;   // image_pyramid.py:21 / :84-85 (ceil division)
         hh = (hh + 1) / 2;
     }
-    h->threads = h->cfg.threads_per_block ? h->cfg.threads_per_block : 128;
-    if (h->threads != 128 && h->threads != 256) {
+    h->threads = h->cfg.threads_per_block ? h->cfg.threads_per_block : DVO_T128;
+    if (h->threads != DVO_T128 && h->threads != 256) {
         h->err = "threads_per_block must be 0, 128 or 256";
         return DVO_ERR_INVALID;
     }
@@ -216,22 +227,15 @@ static int create_impl(dvo_handle* h) {
     h->blocks_per_sm = h->cfg.blocks_per_sm > 0 ? (h->cfg.blocks_per_sm < occ ? h->cfg.blocks_per_sm : occ) : occ;
     h->grid_max = h->sm_count * h->blocks_per_sm;
     DVO_CUDA(h, cudaMalloc(&h->queue, sizeof(int) * kQueueSlots));
-    if (h->cfg.weights == DVO_W_TDIST_REF) {
-        // one level-0 residual plane per CTA of the persistent grid (at most one CTA per pair, so never more than
-        // max_pairs), or per pair in cluster mode (kept to short batches: 256 pairs)
-        h->scratch_stride = h->lplane[0];
-        h->scratch_planes = h->grid_max < h->max_pairs ? h->grid_max : h->max_pairs;
-        if (h->cfg.cluster_size > 1 && h->max_pairs <= kClusterTdistMaxPairs && h->max_pairs > h->scratch_planes)
-            h->scratch_planes = h->max_pairs;
-        DVO_CUDA(h, cudaMalloc(&h->scratch, h->scratch_stride * sizeof(float) * (size_t)h->scratch_planes * kScratchSets));
-    }
     DVO_CUDA(h, cudaMalloc(&h->qt_init, sizeof(float) * 7 * h->max_pairs));
     DVO_CUDA(h, cudaMalloc(&h->qt_last, sizeof(float) * 7 * h->max_pairs));
     DVO_CUDA(h, cudaMalloc(&h->qt_out, sizeof(float) * 7 * h->max_pairs));
     DVO_CUDA(h, cudaMalloc(&h->qt_one, sizeof(float) * 32));
     DVO_CUDA(h, cudaMalloc(&h->stats, sizeof(dvo_pair_stats) * h->max_pairs));
-    DVO_CUDA(h, cudaEventCreate(&h->ev0));
-    DVO_CUDA(h, cudaEventCreate(&h->ev1));
+    for (int i = 0; i < 8; ++i) {
+        DVO_CUDA(h, cudaEventCreate(&h->ev0[i]));
+        DVO_CUDA(h, cudaEventCreate(&h->ev1[i]));
+    }
     return DVO_OK;
 }
 
@@ -312,14 +316,17 @@ extern "C" int dvo_level_intrinsics(const dvo_handle* h, int level, float* k4) {
 extern "C" long long dvo_launch_count(const dvo_handle* h) { return h ? h->launches : 0; }
 
 // ---- pyramids ----------------------------------------------------------------------------------
+// with_gradients (the `roles` of the frames): 0 = used as previous frames only (previous-frame records, no tap
+// records), 1 = both roles, 2 = used as current frames only (tap records, no previous-frame records).
 static int build_levels(dvo_handle* h, int frame_base, int n_frames, int with_gradients, cudaStream_t st) {
+    const bool want_prec = with_gradients != 2;
     for (int l = 1; l < h->levels; ++l) {
         const int groups = (h->lw[l] + 3) / 4 * h->lh[l];
         dim3 grid((groups + 127) / 128, n_frames);
         median3_down_pair_kernel<<<grid, 128, 0, st>>>(
             h->gray[l - 1] + (size_t)frame_base * h->lplane[l - 1], h->gray[l] + (size_t)frame_base * h->lplane[l],
             h->depth[l - 1] + (size_t)frame_base * h->lplane[l - 1], h->depth[l] + (size_t)frame_base * h->lplane[l],
-            h->lw[l - 1], h->lh[l - 1], h->lpitch[l - 1], h->lplane[l - 1], h->lw[l], h->lh[l], h->lpitch[l],
+            want_prec ? h->prec[l] + 2 * (size_t)frame_base * h->lplane[l] : nullptr, h->depth_scale, h->lw[l - 1], h->lh[l - 1], h->lpitch[l - 1], h->lplane[l - 1], h->lw[l], h->lh[l], h->lpitch[l],
             h->lplane[l]);
         h->launches += 1;
     }
@@ -342,16 +349,19 @@ static int build_impl(dvo_handle* h, int frame_base, const uint8_t* img, uint16_
     if (!img || !depth) return fail(h, DVO_ERR_INVALID, "null image pointer");
     if (n_frames < 1 || frame_base < 0 || frame_base + n_frames > h->max_frames)
         return fail(h, DVO_ERR_RANGE, "frame slots out of range");
-    if (clamp && !h->intrinsics_set) return fail(h, DVO_ERR_STATE, "dvo_set_intrinsics must be called first");
+    if (n_frames > 65535) return fail(h, DVO_ERR_RANGE, "at most 65535 frames per build call (the frame index is gridDim.y)");
+    if (!h->intrinsics_set) return fail(h, DVO_ERR_STATE, "dvo_set_intrinsics must be called first");
+    if (with_gradients < 0 || with_gradients > 2) return fail(h, DVO_ERR_INVALID, "with_gradients must be 0, 1 or 2");
     DVO_CUDA(h, cudaSetDevice(h->device));
     const int gpr = (h->W + 3) / 4;
     dim3 grid((gpr * h->H + 255) / 256, n_frames);
     const bool vec = (h->W % 4 == 0) && (((uintptr_t)img & 3) == 0) && (((uintptr_t)depth & 7) == 0);
     uint8_t* g0 = h->gray[0] + (size_t)frame_base * h->lplane[0];
     uint16_t* d0 = h->depth[0] + (size_t)frame_base * h->lplane[0];
+    float* p0 = with_gradients != 2 ? h->prec[0] + 2 * (size_t)frame_base * h->lplane[0] : nullptr;
 #define DVO_LAUNCH_GC(V, B)                                                                                        \
-    gray_clamp_kernel<V, B><<<grid, 256, 0, st>>>(img, depth, g0, d0, h->W, h->H, h->lpitch[0], h->lplane[0],    \
-                                                  h->clamp_thr, clamp ? 1 : 0)
+    gray_clamp_kernel<V, B><<<grid, 256, 0, st>>>(img, depth, g0, d0, p0, h->depth_scale, h->W, h->H, h->lpitch[0], \
+                                                  h->lplane[0], h->clamp_thr, clamp ? 1 : 0)
     if (vec && has_bgr) DVO_LAUNCH_GC(true, true);
     else if (vec) DVO_LAUNCH_GC(true, false);
     else if (has_bgr) DVO_LAUNCH_GC(false, true);
@@ -440,6 +450,7 @@ static void fill_params(const dvo_handle* h, AlignParams& p) {
         g.gray = h->gray[l];
         g.depth = h->depth[l];
         g.rec = h->rec[l];
+        g.prec = h->prec[l];
         g.plane = h->lplane[l];
         g.w = h->lw[l];
         g.h = h->lh[l];
@@ -478,8 +489,6 @@ static void fill_params(const dvo_handle* h, AlignParams& p) {
     p.scale_hi = s_hi;
     p.scale_lo = (float)(h->depth_scale - (double)s_hi);
     p.queue = h->queue;
-    p.scratch = h->scratch;
-    p.scratch_stride = h->scratch_stride;
     // tuning knob (dvo_config.reserved[0]): L1 prefetch distance in rows; 0 = default (2), < 0 = off
     p.prefetch_rows = h->cfg.reserved[0] > 0 ? h->cfg.reserved[0] : (h->cfg.reserved[0] < 0 ? 0 : 2);
     p.prefetch_raw_rows = p.prefetch_rows;
@@ -515,14 +524,13 @@ extern "C" int dvo_estimate(dvo_handle* h, int prev_base, int cur_base, int n_pa
     p.out_qt = out_qt_dev;
     p.stats = stats_dev;
     p.queue = h->queue + h->queue_next;
-    if (h->scratch) p.scratch = h->scratch + (size_t)(h->queue_next % kScratchSets) * h->scratch_stride * (size_t)h->scratch_planes;
-    h->queue_next = (h->queue_next + 1) % (kQueueSlots / kScratchSets * kScratchSets);
+    h->queue_next = (h->queue_next + 1) % kQueueSlots;
     DVO_CUDA(h, cudaMemsetAsync(p.queue, 0, sizeof(int), st));
     const int grid = n_pairs < h->grid_max ? n_pairs : h->grid_max;
     align_fn fn = get_align(h);
     align_fn cfn = (h->cfg.cluster_size > 1 && !h->cfg.use_depth_residual) ? get_cluster(h) : nullptr;
-    if (cfn && h->cfg.weights == DVO_W_TDIST_REF && n_pairs > h->scratch_planes) cfn = nullptr;  // no plane per pair
-    DVO_CUDA(h, cudaEventRecord(h->ev0, st));
+    const int ev = (h->ev_last + 1) & 7;
+    DVO_CUDA(h, cudaEventRecord(h->ev0[ev], st));
     void* args[] = {&p};
     if (cfn) {
         const int C = h->cfg.cluster_size;
@@ -543,8 +551,8 @@ extern "C" int dvo_estimate(dvo_handle* h, int prev_base, int cur_base, int n_pa
     } else {
         DVO_CUDA(h, cudaLaunchKernel((const void*)fn, dim3(grid), dim3(h->threads), args, 0, st));
     }
-    DVO_CUDA(h, cudaEventRecord(h->ev1, st));
-    h->ev_valid = true;
+    DVO_CUDA(h, cudaEventRecord(h->ev1[ev], st));
+    h->ev_last = ev;
     h->launches += 1;
     return DVO_OK;
 }
@@ -571,10 +579,10 @@ extern "C" int dvo_estimate_host(dvo_handle* h, int prev_base, int cur_base, int
 
 extern "C" int dvo_last_estimate_ms(dvo_handle* h, float* ms) {
     if (!h || !ms) return DVO_ERR_INVALID;
-    if (!h->ev_valid) return fail(h, DVO_ERR_STATE, "no estimate has been launched");
+    if (h->ev_last < 0) return fail(h, DVO_ERR_STATE, "no estimate has been launched");
     DVO_CUDA(h, cudaSetDevice(h->device));
-    DVO_CUDA(h, cudaEventSynchronize(h->ev1));
-    DVO_CUDA(h, cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    DVO_CUDA(h, cudaEventSynchronize(h->ev1[h->ev_last]));
+    DVO_CUDA(h, cudaEventElapsedTime(ms, h->ev0[h->ev_last], h->ev1[h->ev_last]));
     return DVO_OK;
 }
 

@@ -4,13 +4,15 @@
 //                         (reference: core/base_dense_visual_odometry.py:58-59)
 //   median3_down_pair_kernel  3x3 median, replicated border, keep even rows/cols (gray and depth level in one launch)
 //                         (reference: utils/image_pyramid.py:19-21, cv2.medianBlur(.,3)[::2, ::2])
+//                         both also write the level's previous-frame planes z, -(0.5 + I/512) (prec_store in
+//                         align_kernel.cuh: camera_model.py:199-200 hoisted out of the Gauss-Newton loop)
 //   sobel3_kernel         3x3 Sobel dx/dy, gain 8, replicated border -> packed 8-byte records {gx, gy, I}
 //                         (reference: utils/jacobian.py:70-71; layout: rec_pack in align_kernel.cuh); the
 //                         intensity rides along so that one 8-byte load per bilinear tap feeds the alignment kernel
 //
 // Plane layout: every level plane is [frame][h][pitch] with pitch a multiple of 16 elements; padding
-// columns stay zero (the planes are cleared once at creation and kernels only write col < w), so a
-// padded depth sample is "no depth".
+// columns stay as initialised at creation (kernels only write col < w): zero in the gray / depth / tap-record
+// planes, "no depth" (z = +inf) in the previous-frame record planes.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -23,8 +25,9 @@ namespace dvo {
 template <bool VEC, bool HAS_BGR>
 __global__ void __launch_bounds__(256) gray_clamp_kernel(const uint8_t* __restrict__ bgr_or_gray,
                                                          uint16_t* __restrict__ depth_io, uint8_t* __restrict__ gray0,
-                                                         uint16_t* __restrict__ depth0, int w, int h, int pitch,
-                                                         size_t plane, int clamp_thr, int do_clamp) {
+                                                         uint16_t* __restrict__ depth0, float* __restrict__ prec0,
+                                                         double depth_scale, int w, int h, int pitch, size_t plane,
+                                                         int clamp_thr, int do_clamp) {
     const int gpr = (w + 3) >> 2;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int frame = blockIdx.y;
@@ -83,6 +86,11 @@ __global__ void __launch_bounds__(256) gray_clamp_kernel(const uint8_t* __restri
         *reinterpret_cast<uchar4*>(gray0 + out) = make_uchar4(gr[0], gr[1], gr[2], gr[3]);
         *reinterpret_cast<ushort4*>(depth0 + out) = make_ushort4(d[0], d[1], d[2], d[3]);
         if (changed) *reinterpret_cast<ushort4*>(depth_io + in_px) = make_ushort4(d[0], d[1], d[2], d[3]);
+        if (prec0) {
+            float* prow = prec0 + 2u * ((size_t)frame * plane + (size_t)row * pitch);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) prec_store(prow, col + k, d[k], gr[k], depth_scale);
+        }
     } else {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -90,8 +98,17 @@ __global__ void __launch_bounds__(256) gray_clamp_kernel(const uint8_t* __restri
                 gray0[out + k] = gr[k];
                 depth0[out + k] = d[k];
                 if (changed) depth_io[in_px + k] = d[k];
+                if (prec0)
+                    prec_store(prec0 + 2u * ((size_t)frame * plane + (size_t)row * pitch), col + k, d[k], gr[k], depth_scale);
             }
     }
+}
+
+// Initial state of a previous-frame record plane: "no depth" everywhere (the padding columns keep it).
+__global__ void prec_fill_kernel(float* __restrict__ p, size_t n_floats) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_floats; i += stride)
+        p[i] = __uint_as_float(((i >> 7) & 1) ? kPrecNoIntensity : kPrecNoDepth);   // 128 z values, 128 c values, ...
 }
 
 // ---- a2 -----------------------------------------------------------------------------------------
@@ -146,7 +163,8 @@ __device__ __forceinline__ void load_row9(const T* __restrict__ row, int k, int 
 // (one block per row left 37-84 % of the threads idle there).
 __global__ void __launch_bounds__(128) median3_down_pair_kernel(const uint8_t* __restrict__ src8, uint8_t* __restrict__ dst8,
                                                                 const uint16_t* __restrict__ src16,
-                                                                uint16_t* __restrict__ dst16, int sw, int sh, int spitch,
+                                                                uint16_t* __restrict__ dst16, float* __restrict__ dprec,
+                                                                double depth_scale, int sw, int sh, int spitch,
                                                                 size_t splane, int dw, int dh, int dpitch, size_t dplane) {
     const int kpr = (dw + 3) >> 2;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -180,10 +198,18 @@ __global__ void __launch_bounds__(128) median3_down_pair_kernel(const uint8_t* _
             (uint32_t)m[0] | ((uint32_t)m[1] << 8) | ((uint32_t)m[2] << 16) | ((uint32_t)m[3] << 24);
         *reinterpret_cast<uint2*>(dst16 + o) =
             make_uint2((uint32_t)n[0] | ((uint32_t)n[1] << 16), (uint32_t)n[2] | ((uint32_t)n[3] << 16));
+        if (dprec) {
+            float* prow = dprec + 2u * ((size_t)frame * dplane + (size_t)oy * dpitch);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) prec_store(prow, ox + j, (unsigned)n[j], (unsigned)m[j], depth_scale);
+        }
     } else {
-        for (int j = 0; j < 4 && ox + j < dw; ++j) {   // padding columns stay zero
+        for (int j = 0; j < 4 && ox + j < dw; ++j) {   // padding columns keep their initial state
             dst8[o + j] = (uint8_t)m[j];
             dst16[o + j] = (uint16_t)n[j];
+            if (dprec)
+                prec_store(dprec + 2u * ((size_t)frame * dplane + (size_t)oy * dpitch), ox + j, (unsigned)n[j], (unsigned)m[j],
+                           depth_scale);
         }
     }
 }

@@ -8,6 +8,14 @@ namespace dvo {
 
 typedef void (*align_fn)(const AlignParams);
 
+// CTAs per SM the 128-thread kernels are compiled for (__launch_bounds__ minimum): 2 = 8 warps per SM at 255 registers
+#ifndef DVO_MINB_128
+#define DVO_MINB_128 2
+#endif
+#ifndef DVO_T128   // developer knob: threads per CTA of the default launch shape
+#define DVO_T128 128
+#endif
+
 // weights x oob_mode for one launch shape (T threads, B CTAs per SM) and one gradient mode G; depth != 0 selects the
 // photometric + depth residual variants (G = 0, unweighted or fixed-threshold Huber only).  nullptr = not built.
 template <int T, int B, int G>

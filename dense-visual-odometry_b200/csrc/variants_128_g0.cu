@@ -2,5 +2,5 @@
 #include "variants.cuh"
 
 namespace dvo {
-align_fn pick_align_128_g0(int w, int oob, int depth) { return pick_variants<128, 2, 0>(w, oob, depth); }
+align_fn pick_align_128_g0(int w, int oob, int depth) { return pick_variants<DVO_T128, DVO_MINB_128, 0>(w, oob, depth); }
 }  // namespace dvo

@@ -126,7 +126,9 @@ def make_config(use_weighter=False, max_increased_steps_allowed=0, sigma=None, t
     cfg.use_depth_residual = 1 if use_depth_residual else 0
     if depth_weight is not None:
         cfg.depth_weight = float(depth_weight)
-    cfg.reserved[0] = int(prefetch_rows)  # tuning knob: L1 prefetch distance in rows (0 = default, < 0 = off, <= 32)
+    if int(prefetch_rows) > 32:   # the planes carry slack rows for at most this read-ahead (dvo_create rejects more)
+        raise ValueError(f"prefetch_rows must be <= 32, got {prefetch_rows}")
+    cfg.reserved[0] = int(prefetch_rows)  # tuning knob: L1 prefetch distance in rows (0 = default, < 0 = off)
     return cfg
 
 
@@ -301,7 +303,7 @@ class RobustDVOB200:
         pdt = torch.as_tensor(pd).to(self._dev)
         self._h.call("dvo_build_pyramids_gray", ps, C.c_void_p(pgt.data_ptr()), C.c_void_p(pdt.data_ptr()), 1,
                      1 if self._approx else 0, st)
-        self._h.call("dvo_build_pyramids_gray", cs, C.c_void_p(g.data_ptr()), C.c_void_p(d.data_ptr()), 1, 1, st)
+        self._h.call("dvo_build_pyramids_gray", cs, C.c_void_p(g.data_ptr()), C.c_void_p(d.data_ptr()), 1, 2, st)
         torch.cuda.current_stream(self._dev).synchronize()
         self._hook_ready = True
 
@@ -388,7 +390,9 @@ class PairBatchAligner:
         self.max_pairs = int(max_pairs)
         self.levels = int(levels)
         self._cfg = make_config(**cfg_kwargs)
-        self._prev_grad = 1 if cfg_kwargs.get("approximate_image2_gradient") else 0  # I1 records are read then
+        # roles of the frames (dvo_build_pyramids, with_gradients): previous frames 0 (their own tap records are read
+        # only with approximate_image2_gradient: 1), current frames 2 (tap records only)
+        self._prev_grad = 1 if cfg_kwargs.get("approximate_image2_gradient") else 0
         self._h = _Handle(device, height, width, levels, 2 * self.max_pairs, self.max_pairs, self._cfg)
         fx, fy, cx, cy, scale = _intrinsics_of(camera_model)
         self._h.call("dvo_set_intrinsics", fx, fy, cx, cy, scale)
@@ -415,10 +419,10 @@ class PairBatchAligner:
         if isinstance(bgr_prev, np.ndarray) or not bgr_prev.is_cuda:
             bp, dp, bc, dc = self._as_host_tensors(bgr_prev, depth_prev, bgr_cur, depth_cur)
             self._h.call("dvo_build_pyramids_host", 0, self._ptr(bp), self._ptr(dp), B, self._prev_grad, st)
-            self._h.call("dvo_build_pyramids_host", self.max_pairs, self._ptr(bc), self._ptr(dc), B, 1, st)
+            self._h.call("dvo_build_pyramids_host", self.max_pairs, self._ptr(bc), self._ptr(dc), B, 2, st)
         else:
             self._h.call("dvo_build_pyramids", 0, self._ptr(bgr_prev), self._ptr(depth_prev), B, self._prev_grad, st)
-            self._h.call("dvo_build_pyramids", self.max_pairs, self._ptr(bgr_cur), self._ptr(depth_cur), B, 1, st)
+            self._h.call("dvo_build_pyramids", self.max_pairs, self._ptr(bgr_cur), self._ptr(depth_cur), B, 2, st)
         self._B = B
 
     def _as_host_tensors(self, *arrays):
@@ -487,7 +491,7 @@ class PairBatchAligner:
             ev.record(cs)
             s.wait_event(ev)
             self._h.call("dvo_build_pyramids_staged", lo, n, self._prev_grad, sp)
-            self._h.call("dvo_build_pyramids_staged", self.max_pairs + lo, n, 1, sp)
+            self._h.call("dvo_build_pyramids_staged", self.max_pairs + lo, n, 2, sp)
             init_ptr = self._ptr(init_dev[lo]) if init_dev is not None else None
             self._h.call("dvo_estimate", lo, self.max_pairs + lo, n, init_ptr, None, self._ptr(self._qt[lo]),
                          self._ptr(self._stats[lo]), sp)

@@ -15,8 +15,9 @@
  *    (pinned memory makes the copies asynchronous).  `stream` is a cudaStream_t passed as void*
  *    (NULL = the legacy default stream).  Calls only enqueue work unless stated otherwise.
  *  - A handle is bound to one device and is not thread-safe: one handle per GPU/stream.
- *  - Frames live in handle-owned "frame slots" 0..max_frames-1 (all pyramid levels, plus gradient
- *    planes).  A pair p of an estimate call aligns slot prev_base+p (previous frame, provides
+ *  - Frames live in handle-owned "frame slots" 0..max_frames-1 (all pyramid levels, plus what the two roles
+ *    of a frame need: metric depth + intensity planes as PREVIOUS frame, packed gradient + intensity records as
+ *    CURRENT frame).  A pair p of an estimate call aligns slot prev_base+p (previous frame, provides
  *    intensity + depth) against slot cur_base+p (current frame, provides intensity + gradients).
  *    Independent pairs: prev_base = 0, cur_base = B.  A sequence: prev_base = 0, cur_base = 1.
  *  - Poses cross the boundary the way the reference's `Se3` stores them
@@ -78,8 +79,8 @@ typedef struct dvo_config {
                                           * PREVIOUS frame's Sobel gradients at the unwarped pixel; frames used as
                                           * "previous" must then be built with_gradients != 0. default 0 */
     int32_t cluster_size;        /* 0/1 = one CTA per pair (throughput); 2, 4, 8 or 16 = one thread-block cluster per
-                                  * pair (latency of single pairs and short batches); ignored with the Huber/MAD weights, with
-                                  * use_depth_residual, and for t-distribution batches of more pairs than residual planes exist */
+                                  * pair (latency of single pairs and short batches); ignored with the Huber/MAD weights and
+                                  * with use_depth_residual */
     int32_t tdist_mean;          /* extension, with DVO_W_TDIST_REF only: 1 = the textbook t-distribution scale
                                   * (MEAN of the weighted squared residuals) instead of the reference's sum (default 0) */
     int32_t use_depth_residual;  /* extension, not in the reference: 1 = add the depth (geometric) residual
@@ -88,7 +89,7 @@ typedef struct dvo_config {
                                   * default 0 */
     float depth_weight;          /* lambda_Z: a depth residual of 1/sqrt(lambda_Z) metres weighs like one grey level.
                                   * default 2500 (2 cm) */
-    int32_t reserved[1];         /* tuning: [0] L1 prefetch distance in rows (0 default, < 0 off) */
+    int32_t reserved[1];         /* tuning: [0] L1 prefetch distance in rows (0 default, < 0 off, at most 32) */
 } dvo_config;
 
 /* Per-pair statistics written by dvo_estimate (index = pyramid level). 128 bytes. */
@@ -120,8 +121,12 @@ int dvo_set_intrinsics(dvo_handle* h, float fx, float fy, float cx, float cy, do
 /* Replaces BaseDenseVisualOdometry.step's preprocessing (base_dense_visual_odometry.py:58-59: BGR->gray,
  * far depth -> 0 IN PLACE) followed by _build_pyramids (cpu_...py:44-52 -> image_pyramid.py:19-54) and
  * _setup's Sobel planes (cpu_...py:58 -> jacobian.py:70-71) for n_frames frames stored in slots
- * frame_base..frame_base+n_frames-1.  bgr: [n,H,W,3] u8, depth: [n,H,W] u16. with_gradients != 0 also
- * builds the gradient planes (needed for frames used as "current"). */
+ * frame_base..frame_base+n_frames-1.  bgr: [n,H,W,3] u8, depth: [n,H,W] u16.  with_gradients names the role(s)
+ * the frames will play: 0 = previous frames only (no gradient planes), 1 = both roles (a sequence: every frame is
+ * first "current", then "previous"), 2 = current frames only (gradient planes, no metric-depth planes).
+ * dvo_set_intrinsics must have been called: the depth scale enters the previous-frame planes
+ * (camera_model.py:199-200, z = depth * depth_scale, is evaluated here, once per frame, not per iteration). */
+/* At most 65535 frames per call. */
 int dvo_build_pyramids(dvo_handle* h, int frame_base, const uint8_t* bgr_dev, uint16_t* depth_dev, int n_frames,
                        int with_gradients, void* stream);
 /* Same from a gray image, no clamp: the backend hook `_build_pyramids(gray_image, depth_image)`
@@ -151,8 +156,8 @@ int dvo_depth_clamp_threshold(const dvo_handle* h, int* threshold);
 int dvo_estimate(dvo_handle* h, int prev_base, int cur_base, int n_pairs, const float* init_qt_dev,
                  const float* last_qt_dev, float* out_qt_dev, dvo_pair_stats* stats_dev, void* stream);
 /* Calls on DIFFERENT streams may be in flight together (a caller pipelining host->device copies of the
- * next pairs behind the estimate of the previous ones): use at most 3 streams, round-robin, and disjoint
- * frame slots / output ranges per call. */
+ * next pairs behind the estimate of the previous ones), with disjoint frame slots / output ranges per call; the
+ * only per-launch state is one of 256 work counters, so at most 256 launches may be pending at a time. */
 /* Same, results copied to host memory (pinned => asynchronous); waits for nothing. */
 int dvo_estimate_host(dvo_handle* h, int prev_base, int cur_base, int n_pairs, const float* init_qt_host,
                       const float* last_qt_host, float* out_qt_host, dvo_pair_stats* stats_host, void* stream);
@@ -185,8 +190,9 @@ int dvo_level_intrinsics(const dvo_handle* h, int level, float* k4);
 /* Number of kernel launches this handle has issued (for bench.py's gpu_launches). */
 long long dvo_launch_count(const dvo_handle* h);
 
-/* Timing of the most recent dvo_estimate kernel on its stream, measured with CUDA events recorded
- * around the launch.  Synchronises on the end event. */
+/* Timing of the most recently LAUNCHED dvo_estimate kernel, measured with CUDA events recorded around that launch
+ * on its stream (every launch has its own pair of events).  Synchronises on the end event.  With several
+ * launches in flight on different streams the interval includes time the kernel shared the GPU with the others. */
 int dvo_last_estimate_ms(dvo_handle* h, float* ms);
 
 #ifdef __cplusplus
