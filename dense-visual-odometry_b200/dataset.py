@@ -179,16 +179,34 @@ def run_sequence(colors: np.ndarray, depths: np.ndarray, camera_model, levels: i
 
     n = colors.shape[0]
     init = initial_pose if initial_pose is not None else Se3.identity()
+    failed = []                       # frames without a pose of their own (they repeat the previous one)
     if batch:
         h, w = depths.shape[1:]
         seq = SequenceAligner(camera_model, h, w, levels, max_frames=n, **dvo_kwargs)
-        rel, _ = seq.align(colors, depths)
+        rel, stats = seq.align(colors, depths)
         rel = [pose_to_qt(Se3.identity())] + [r for r in rel]
+        # A pair whose estimate is not finite: step() returns None for it, KEEPS the previous frame and aligns the next
+        # frame against that one (base_dense_visual_odometry.py:75-85).  The same here: the frame gets the identity
+        # and the following frame is re-estimated against the last good one (its pyramids are still resident).
+        good = 0                      # last frame with a pose
+        for f in range(1, n):
+            if good == f - 1:         # the batch estimated exactly this pair
+                q = rel[f] if (np.all(np.isfinite(rel[f])) and not int(stats["flags"][f - 1]) & 1) else None
+            else:
+                q = seq.estimate_pair(good, f)
+            if q is not None:
+                rel[f] = q
+                good = f
+            else:
+                failed.append(f)
+                rel[f] = pose_to_qt(Se3.identity())
     else:
         dvo = RobustDVOB200(camera_model, init, levels, **dvo_kwargs)
         rel = []
         for i in range(n):
             T = dvo.step(colors[i], depths[i])
+            if T is None:
+                failed.append(i)
             rel.append(pose_to_qt(T if T is not None else Se3.identity()))
     traj = chain_poses(rel[1:], init)
     errors = []
@@ -198,4 +216,5 @@ def run_sequence(colors: np.ndarray, depths: np.ndarray, camera_model, levels: i
         else:
             errors.append("N/A")
     return {"estimated_transforms": [Se3.from_qt(r).log().reshape(-1).tolist() for r in rel],
-            "estimated_poses": [p.log().reshape(-1).tolist() for p in traj], "errors": errors, "trajectory": traj}
+            "estimated_poses": [p.log().reshape(-1).tolist() for p in traj], "errors": errors, "trajectory": traj,
+            "failed_frames": failed}

@@ -180,6 +180,7 @@ class RobustDVOB200:
         self._prev_slot = 0           # step(): slot holding the previous frame
         self._hook_slots = (2, 3)     # _build_pyramids hook: (prev, cur)
         self._host_prev = None        # lazily fetched (gray, depth) of the previous frame
+        self._upload_done = None      # event: the last frame's copies out of the pinned staging buffers have finished
         self.last_stats = None
         if height is not None and width is not None:
             self._ensure(int(height), int(width))
@@ -233,10 +234,16 @@ class RobustDVOB200:
             depth16 = depth_image
         st = _stream_ptr(torch, self._dev)
         cur_slot = 1 - self._prev_slot
+        # the previous frame's asynchronous copies out of the pinned staging buffers must be over before they are
+        # rewritten (the first-frame path returns without synchronising the stream)
+        if self._upload_done is not None:
+            self._upload_done.synchronize()
         self._pin_bgr.numpy()[...] = color_image
         self._pin_depth.numpy()[...] = depth16
         self._h.call("dvo_build_pyramids_host", cur_slot, C.c_void_p(self._pin_bgr.data_ptr()),
                      C.c_void_p(self._pin_depth.data_ptr()), 1, 1, st)
+        self._upload_done = torch.cuda.Event()
+        self._upload_done.record(torch.cuda.current_stream(self._dev))
         # the reference zeroes far depth in the caller's array (base_dense_visual_odometry.py:59)
         if self._clamp_thr < 65536:
             depth_image[depth_image >= self._clamp_thr] = 0
@@ -599,6 +606,18 @@ class SequenceAligner:
             cur.wait_stream(s)
         cur.wait_stream(cs)
         return self._pin_qt[:N - 1].numpy().copy(), stats_to_numpy(self._pin_stats[:N - 1].numpy())
+
+    def estimate_pair(self, prev_frame: int, cur_frame: int):
+        """One more estimate between two frames of the last align() call (their pyramids are still resident):
+        qt [7] taking frame prev_frame's camera to frame cur_frame's, or None if it is not finite."""
+        torch = self._torch
+        if not (0 <= prev_frame < self.max_frames and 0 <= cur_frame < self.max_frames):
+            raise ValueError("frame index out of range")
+        st = _stream_ptr(torch, self._dev)
+        self._h.call("dvo_estimate", prev_frame, cur_frame, 1, None, None, C.c_void_p(self._qt[0].data_ptr()),
+                     C.c_void_p(self._stats[0].data_ptr()), st)
+        q = self._qt[0].cpu().numpy().copy()
+        return q if np.all(np.isfinite(q)) else None
 
     def launch_count(self) -> int:
         return self._h.launch_count()
