@@ -6,7 +6,7 @@
 //                         (reference: utils/image_pyramid.py:19-21, cv2.medianBlur(.,3)[::2, ::2])
 //                         both also write the level's previous-frame planes z, -(0.5 + I/512) (prec_store in
 //                         align_kernel.cuh: camera_model.py:199-200 hoisted out of the Gauss-Newton loop)
-//   sobel3_kernel         3x3 Sobel dx/dy, gain 8, replicated border -> packed 8-byte records {gx, gy, I}
+//   sobel3_kernel         3x3 Sobel dx/dy, gain 8, replicated border -> packed 8-byte records {gx, gy, I, depth}
 //                         (reference: utils/jacobian.py:70-71; layout: rec_pack in align_kernel.cuh); the
 //                         intensity rides along so that one 8-byte load per bilinear tap feeds the alignment kernel
 //
@@ -229,8 +229,8 @@ __device__ __forceinline__ void load_row6(const uint8_t* __restrict__ row, int x
     v[5] = (int)__ldg(row + min(x0 + 4, w - 1));
 }
 
-__global__ void __launch_bounds__(128) sobel3_kernel(const uint8_t* __restrict__ gray, uint2* __restrict__ rec,
-                                                     int w, int h, int pitch, size_t plane) {
+__global__ void __launch_bounds__(128) sobel3_kernel(const uint8_t* __restrict__ gray, const uint16_t* __restrict__ depth,
+                                                     uint2* __restrict__ rec, int w, int h, int pitch, size_t plane) {
     // threads numbered linearly over (row, 4-pixel group): narrow levels still fill their blocks
     const int gpr = (w + 3) >> 2;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -243,12 +243,16 @@ __global__ void __launch_bounds__(128) sobel3_kernel(const uint8_t* __restrict__
     load_row6(s + (size_t)max(y - 1, 0) * pitch, x0, w, a);
     load_row6(s + (size_t)y * pitch, x0, w, b);
     load_row6(s + (size_t)min(y + 1, h - 1) * pitch, x0, w, c);
+    // the pixel's depth rides in the record too (padding columns of the depth plane are zero, and so are the four
+    // values of a partial group beyond the image: the 8-byte load stays inside the row's pitch)
+    const uint2 dw = __ldg(reinterpret_cast<const uint2*>(depth + (size_t)frame * plane + (size_t)y * pitch + x0));
+    const unsigned dd[4] = {dw.x & 0xffffu, dw.x >> 16, dw.y & 0xffffu, dw.y >> 16};
     uint2 out[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int gx = (a[j + 2] + 2 * b[j + 2] + c[j + 2]) - (a[j] + 2 * b[j] + c[j]);
         const int gy = (c[j] + 2 * c[j + 1] + c[j + 2]) - (a[j] + 2 * a[j + 1] + a[j + 2]);
-        out[j] = rec_pack(gx, gy, b[j + 1]);
+        out[j] = rec_pack(gx, gy, b[j + 1], dd[j]);
     }
     uint2* d = rec + (size_t)frame * plane + (size_t)y * pitch + x0;
     if (x0 + 3 < w) {
