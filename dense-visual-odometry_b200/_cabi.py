@@ -64,6 +64,7 @@ SYMBOLS = {
     "dvo_level_intrinsics": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float)]),
     "dvo_launch_count": (C.c_longlong, [_P]),
     "dvo_last_estimate_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "dvo_debug_bounds_violations": (C.c_int, [_P, C.POINTER(C.c_ulonglong)]),
 }
 
 _lib = None

@@ -26,6 +26,8 @@ struct dvo_handle {
     int clamp_thr = 65536;
     int lw[DVO_MAX_LEVELS]{}, lh[DVO_MAX_LEVELS]{}, lpitch[DVO_MAX_LEVELS]{};
     size_t lplane[DVO_MAX_LEVELS]{};
+    size_t n_rec[DVO_MAX_LEVELS]{}, n_raw[DVO_MAX_LEVELS]{};   // elements allocated per level (frames + slack rows)
+    unsigned long long* dbg_violations = nullptr;            // DVO_BOUNDS_CHECK builds only
     uint8_t* gray[DVO_MAX_LEVELS]{};
     uint16_t* depth[DVO_MAX_LEVELS]{};
     uint2* rec[DVO_MAX_LEVELS]{};
@@ -101,7 +103,9 @@ static align_fn get_align(const dvo_handle* h) {
 // Cluster-mode kernel (one thread-block cluster per pair); not built for the Huber/MAD weights.
 static align_fn get_cluster(const dvo_handle* h) {
     const int w = h->cfg.weights, o = h->cfg.oob_mode;
-    return h->cfg.approximate_image2_gradient ? pick_cluster_g1(w, o) : pick_cluster_g0(w, o);
+    const int dz = h->cfg.use_depth_residual ? 1 : 0;
+    if (h->cfg.approximate_image2_gradient) return dz ? nullptr : pick_cluster_g1(w, o);
+    return pick_cluster_g0(w, o, dz);
 }
 
 typedef void (*dump_fn)(const AlignParams, int, int, int, const float*, float, float*, float*, uint8_t*, uint8_t*,
@@ -138,6 +142,7 @@ extern "C" int dvo_destroy(dvo_handle* h) {
         cudaFree(h->prec[l]);
     }
     cudaFree(h->queue);
+    cudaFree(h->dbg_violations);
     cudaFree(h->stage_bgr);
     cudaFree(h->stage_depth);
     cudaFree(h->qt_init);
@@ -183,6 +188,8 @@ static int create_impl(dvo_handle* h) {
         // One row more than needed is allocated for each.
         const size_t n_rec = n + (size_t)(kMaxPrefetchRows + 3) * (size_t)h->lpitch[l];
         const size_t n_raw = n + (size_t)(kMaxPrefetchRows + 4) * (size_t)h->lpitch[l];
+        h->n_rec[l] = n_rec;
+        h->n_raw[l] = n_raw;
         DVO_CUDA(h, cudaMalloc(&h->gray[l], n_raw));
         DVO_CUDA(h, cudaMalloc(&h->depth[l], n_raw * sizeof(uint16_t)));
         DVO_CUDA(h, cudaMalloc(&h->rec[l], n_rec * sizeof(uint2)));
@@ -227,6 +234,10 @@ static int create_impl(dvo_handle* h) {
     h->blocks_per_sm = h->cfg.blocks_per_sm > 0 ? (h->cfg.blocks_per_sm < occ ? h->cfg.blocks_per_sm : occ) : occ;
     h->grid_max = h->sm_count * h->blocks_per_sm;
     DVO_CUDA(h, cudaMalloc(&h->queue, sizeof(int) * kQueueSlots));
+#ifdef DVO_BOUNDS_CHECK
+    DVO_CUDA(h, cudaMalloc(&h->dbg_violations, sizeof(unsigned long long)));
+    DVO_CUDA(h, cudaMemset(h->dbg_violations, 0, sizeof(unsigned long long)));
+#endif
     DVO_CUDA(h, cudaMalloc(&h->qt_init, sizeof(float) * 7 * h->max_pairs));
     DVO_CUDA(h, cudaMalloc(&h->qt_last, sizeof(float) * 7 * h->max_pairs));
     DVO_CUDA(h, cudaMalloc(&h->qt_out, sizeof(float) * 7 * h->max_pairs));
@@ -472,6 +483,17 @@ static void fill_params(const dvo_handle* h, AlignParams& p) {
             g.chunks_per_strip = nw * k;
             g.chunk_rows = (h->lh[l] + g.chunks_per_strip - 1) / g.chunks_per_strip;
         }
+#ifdef DVO_BOUNDS_CHECK
+        p.dbg_rec_lo[l] = reinterpret_cast<const char*>(h->rec[l]);
+        p.dbg_rec_hi[l] = p.dbg_rec_lo[l] + h->n_rec[l] * sizeof(uint2);
+        p.dbg_prec_lo[l] = reinterpret_cast<const char*>(h->prec[l]);
+        p.dbg_prec_hi[l] = p.dbg_prec_lo[l] + 2 * h->n_raw[l] * sizeof(float);
+        {   // negative control: DVO_DEBUG_SHRINK_ROWS pretends the allocations are that many rows shorter
+            static const int shrink = [] { const char* e = getenv("DVO_DEBUG_SHRINK_ROWS"); return e ? atoi(e) : 0; }();
+            p.dbg_rec_hi[l] -= (size_t)shrink * h->lpitch[l] * sizeof(uint2);
+            p.dbg_prec_hi[l] -= (size_t)shrink * h->lpitch[l] * 2 * sizeof(float);
+        }
+#endif
         g.fx = h->k4[l][0]; g.fy = h->k4[l][1]; g.cx = h->k4[l][2]; g.cy = h->k4[l][3];
         g.ifx = h->kinv4[l][0]; g.ify = h->kinv4[l][1]; g.icx = h->kinv4[l][2]; g.icy = h->kinv4[l][3];
     }
@@ -502,6 +524,21 @@ static void fill_params(const dvo_handle* h, AlignParams& p) {
         p.prefetch_res_rows = res_rows;
     }
     p.depth_weight = h->cfg.depth_weight;
+#ifdef DVO_BOUNDS_CHECK
+    p.dbg_violations = h->dbg_violations;
+#endif
+}
+
+extern "C" int dvo_debug_bounds_violations(dvo_handle* h, unsigned long long* count) {
+    if (!h || !count) return DVO_ERR_INVALID;
+#ifdef DVO_BOUNDS_CHECK
+    DVO_CUDA(h, cudaSetDevice(h->device));
+    DVO_CUDA(h, cudaDeviceSynchronize());
+    DVO_CUDA(h, cudaMemcpy(count, h->dbg_violations, sizeof(*count), cudaMemcpyDeviceToHost));
+    return DVO_OK;
+#else
+    return fail(h, DVO_ERR_STATE, "the library was built without -DDVO_BOUNDS_CHECK");
+#endif
 }
 
 extern "C" int dvo_estimate(dvo_handle* h, int prev_base, int cur_base, int n_pairs, const float* init_qt_dev,
@@ -529,7 +566,7 @@ extern "C" int dvo_estimate(dvo_handle* h, int prev_base, int cur_base, int n_pa
     DVO_CUDA(h, cudaMemsetAsync(p.queue, 0, sizeof(int), st));
     const int grid = n_pairs < h->grid_max ? n_pairs : h->grid_max;
     align_fn fn = get_align(h);
-    align_fn cfn = (h->cfg.cluster_size > 1 && !h->cfg.use_depth_residual) ? get_cluster(h) : nullptr;
+    align_fn cfn = h->cfg.cluster_size > 1 ? get_cluster(h) : nullptr;
     const int ev = (h->ev_last + 1) & 7;
     DVO_CUDA(h, cudaEventRecord(h->ev0[ev], st));
     void* args[] = {&p};

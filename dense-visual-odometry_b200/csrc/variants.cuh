@@ -53,13 +53,26 @@ static align_fn pick_variants(int w, int oob, int depth) {
 }
 
 // Cluster-mode kernels (one thread-block cluster per pair) for one gradient mode; not built for Huber/MAD.
+// depth != 0: the photometric + depth residual variants (G = 0, unweighted or fixed-threshold Huber).
 template <int G>
-static align_fn pick_cluster_variants(int w, int oob) {
+static align_fn pick_cluster_variants(int w, int oob, int depth) {
 #ifdef DVO_FAST_BUILD
-    if (G == 0 && w == DVO_W_NONE && oob == DVO_OOB_INCLUSIVE)
+    if (G == 0 && !depth && w == DVO_W_NONE && oob == DVO_OOB_INCLUSIVE)
         return (align_fn)align_cluster_kernel<DVO_W_NONE, DVO_OOB_INCLUSIVE, G>;
     return nullptr;
 #else
+    if (depth) {
+        if constexpr (G == 0) {
+#define DVO_PICKCD(WM, OM) \
+    if (w == WM && oob == OM) return (align_fn)align_cluster_kernel<WM, OM, 0, 1>;
+            DVO_PICKCD(DVO_W_NONE, DVO_OOB_INCLUSIVE)
+            DVO_PICKCD(DVO_W_NONE, DVO_OOB_STRICT)
+            DVO_PICKCD(DVO_W_HUBER, DVO_OOB_INCLUSIVE)
+            DVO_PICKCD(DVO_W_HUBER, DVO_OOB_STRICT)
+#undef DVO_PICKCD
+        }
+        return nullptr;
+    }
 #define DVO_PICKC(WM, OM) \
     if (w == WM && oob == OM) return (align_fn)align_cluster_kernel<WM, OM, G>;
     DVO_PICKC(DVO_W_NONE, DVO_OOB_INCLUSIVE)
@@ -78,7 +91,7 @@ align_fn pick_align_128_g0(int w, int oob, int depth);
 align_fn pick_align_128_g1(int w, int oob);
 align_fn pick_align_256_g0(int w, int oob, int depth);
 align_fn pick_align_256_g1(int w, int oob);
-align_fn pick_cluster_g0(int w, int oob);
+align_fn pick_cluster_g0(int w, int oob, int depth);
 align_fn pick_cluster_g1(int w, int oob);
 
 }  // namespace dvo

@@ -2,5 +2,5 @@
 #include "variants.cuh"
 
 namespace dvo {
-align_fn pick_cluster_g1(int w, int oob) { return pick_cluster_variants<1>(w, oob); }
+align_fn pick_cluster_g1(int w, int oob) { return pick_cluster_variants<1>(w, oob, 0); }
 }  // namespace dvo

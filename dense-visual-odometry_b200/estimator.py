@@ -81,6 +81,12 @@ class _Handle:
         self.call("dvo_last_estimate_ms", C.byref(ms))
         return ms.value
 
+    def bounds_violations(self) -> int:
+        """Debug builds (-DDVO_BOUNDS_CHECK): out-of-allocation addresses the alignment kernel has formed so far."""
+        n = C.c_ulonglong()
+        self.call("dvo_debug_bounds_violations", C.byref(n))
+        return int(n.value)
+
     def close(self):
         if getattr(self, "ptr", None):
             self.lib.dvo_destroy(self.ptr)
@@ -169,7 +175,7 @@ class RobustDVOB200:
         self._max_distance = max_distance
         self._device = device
         # one pair at a time: a thread-block cluster of `cluster_size` CTAs shares the pair (8.1 ms -> 2.0 ms per
-        # 640x480 pose at 8); Huber/MAD weights and the depth residual fall back to one 256-thread CTA
+        # 640x480 pose at 8); the Huber/MAD weights fall back to one 256-thread CTA
         self._cfg = make_config(use_weighter, max_increased_steps_allowed, sigma, tolerance, max_iterations, weights,
                                 oob_mode, huber_k, max_distance, threads_per_block=256,
                                 approximate_image2_gradient=approximate_image2_gradient, cluster_size=cluster_size,

@@ -79,13 +79,12 @@ typedef struct dvo_config {
                                           * PREVIOUS frame's Sobel gradients at the unwarped pixel; frames used as
                                           * "previous" must then be built with_gradients != 0. default 0 */
     int32_t cluster_size;        /* 0/1 = one CTA per pair (throughput); 2, 4, 8 or 16 = one thread-block cluster per
-                                  * pair (latency of single pairs and short batches); ignored with the Huber/MAD weights and
-                                  * with use_depth_residual */
+                                  * pair (latency of single pairs and short batches); ignored with the Huber/MAD weights */
     int32_t tdist_mean;          /* extension, with DVO_W_TDIST_REF only: 1 = the textbook t-distribution scale
                                   * (MEAN of the weighted squared residuals) instead of the reference's sum (default 0) */
     int32_t use_depth_residual;  /* extension, not in the reference: 1 = add the depth (geometric) residual
                                   * r_Z = Z2(w(x)) - [T P]_z to the normal equations with weight depth_weight; available
-                                  * with DVO_W_NONE / DVO_W_HUBER, approximate_image2_gradient = 0, one CTA per pair.
+                                  * with DVO_W_NONE / DVO_W_HUBER and approximate_image2_gradient = 0.
                                   * default 0 */
     float depth_weight;          /* lambda_Z: a depth residual of 1/sqrt(lambda_Z) metres weighs like one grey level.
                                   * default 2500 (2 cm) */
@@ -194,6 +193,11 @@ long long dvo_launch_count(const dvo_handle* h);
  * on its stream (every launch has its own pair of events).  Synchronises on the end event.  With several
  * launches in flight on different streams the interval includes time the kernel shared the GPU with the others. */
 int dvo_last_estimate_ms(dvo_handle* h, float* ms);
+
+/* Debug builds only (nvcc -DDVO_BOUNDS_CHECK; tools/sanitize_cases.py): the alignment kernel tests every load and
+ * prefetch address of its streaming pass against the extents of the handle's allocations; this returns the number of
+ * misses since dvo_create (after a device synchronisation).  DVO_ERR_STATE in a normal build. */
+int dvo_debug_bounds_violations(dvo_handle* h, unsigned long long* count);
 
 #ifdef __cplusplus
 }

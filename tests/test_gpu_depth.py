@@ -150,12 +150,12 @@ def test_depth_pose_batch_synthetic_vs_oracle_and_truth(dvo_mod, golden_dir, wei
     assert np.array_equal(q1[0], qt[2])
 
 
-def test_depth_high_resolution_five_levels(dvo_mod):
-    """BASELINE.json configs[4]: a 1280x720 pair, 5-level pyramid, photometric + depth residual: the pose against the
-    oracle, and the depth term per pixel at the coarsest and the finest level."""
+@pytest.mark.parametrize("h,w", [(720, 1280), (1080, 1920)])
+def test_depth_high_resolution_five_levels(dvo_mod, h, w):
+    """BASELINE.json configs[4]: a 1280x720 and a 1920x1080 pair, 5-level pyramid, photometric + depth residual: the
+    pose against the oracle, and the depth term per pixel at the coarsest and the finest level."""
     from dense_visual_odometry_b200.synthetic import make_pairs_numpy, TUM_FR1
     m = dvo_mod
-    h, w = 720, 1280
     s = w / 640.0
     K = (TUM_FR1[0] * s, TUM_FR1[1] * s, TUM_FR1[2] * s, TUM_FR1[3] * s)
     d = make_pairs_numpy([5], height=h, width=w, K=K)
@@ -182,7 +182,7 @@ def test_depth_high_resolution_five_levels(dvo_mod):
     for lv in (4, 0):
         ld = O.prepare_level(Km, d["depth_scale"], pg[lv], pd[lv], cg[lv], lv, depth_cur=cd[lv])
         _compare_depth_level(est, ld, m.Se3.identity(), lv, O.OOB_INCLUSIVE, 2500.0, report)
-    print("720p depth-term parity:", report)
+    print(f"{w}x{h} depth-term parity:", report)
 
 
 def test_depth_option_errors_are_loud(dvo_mod):
