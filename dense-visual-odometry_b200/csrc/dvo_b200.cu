@@ -33,8 +33,12 @@ struct dvo_handle {
     uint2* rec[DVO_MAX_LEVELS]{};
     float* prec[DVO_MAX_LEVELS]{};   // previous-frame planes: z and -(0.5 + I/512), 2 floats per pixel (align_kernel.cuh, prec_index)
     float k4[DVO_MAX_LEVELS][4]{}, kinv4[DVO_MAX_LEVELS][4]{};
-    int* queue = nullptr;   // kQueueSlots pair counters; concurrent dvo_estimate calls (different streams) rotate through them
+    int* queue = nullptr;   // kQueueSlots x 4 work-queue counters; concurrent dvo_estimate calls (different streams) rotate through them
     int queue_next = 0;
+    unsigned long long* ring = nullptr;   // work-queue cells, one per frame slot (a launch uses those of its previous frames)
+    int* dlist = nullptr;                 // pairs left to the tail kernel, one entry per frame slot
+    PairState* pstate = nullptr;          // saved Gauss-Newton state of a pair between two time slices, one per frame slot
+    float* chunk_sums = nullptr;          // per-chunk sums of a pair's current pass (canonical summation order), per frame slot
     int sm_count = 0, threads = 256, blocks_per_sm = 2, grid_max = 0;
     uint8_t* stage_bgr = nullptr;
     uint16_t* stage_depth = nullptr;
@@ -108,6 +112,15 @@ static align_fn get_cluster(const dvo_handle* h) {
     return pick_cluster_g0(w, o, dz);
 }
 
+// Tail kernel (one thread-block cluster per pair the persistent kernel left unfinished); 128-thread shape only.
+static align_fn get_tail(const dvo_handle* h) {
+    const int w = h->cfg.weights, o = h->cfg.oob_mode;
+    const int dz = h->cfg.use_depth_residual ? 1 : 0;
+    if (h->threads != 128 || w == DVO_W_HUBER_MAD) return nullptr;
+    if (h->cfg.approximate_image2_gradient) return dz ? nullptr : pick_tail_g1(w, o);
+    return pick_tail_g0(w, o, dz);
+}
+
 typedef void (*dump_fn)(const AlignParams, int, int, int, const float*, float, float*, float*, uint8_t*, uint8_t*,
                         double*);
 static dump_fn get_dump(const dvo_handle* h) {
@@ -142,6 +155,10 @@ extern "C" int dvo_destroy(dvo_handle* h) {
         cudaFree(h->prec[l]);
     }
     cudaFree(h->queue);
+    cudaFree(h->ring);
+    cudaFree(h->dlist);
+    cudaFree(h->pstate);
+    cudaFree(h->chunk_sums);
     cudaFree(h->dbg_violations);
     cudaFree(h->stage_bgr);
     cudaFree(h->stage_depth);
@@ -233,7 +250,11 @@ static int create_impl(dvo_handle* h) {
     if (occ < 1) occ = 1;
     h->blocks_per_sm = h->cfg.blocks_per_sm > 0 ? (h->cfg.blocks_per_sm < occ ? h->cfg.blocks_per_sm : occ) : occ;
     h->grid_max = h->sm_count * h->blocks_per_sm;
-    DVO_CUDA(h, cudaMalloc(&h->queue, sizeof(int) * kQueueSlots));
+    DVO_CUDA(h, cudaMalloc(&h->queue, sizeof(int) * 8 * kQueueSlots));
+    DVO_CUDA(h, cudaMalloc(&h->dlist, sizeof(int) * h->max_frames));
+    DVO_CUDA(h, cudaMalloc(&h->ring, sizeof(unsigned long long) * h->max_frames));
+    DVO_CUDA(h, cudaMalloc(&h->pstate, sizeof(PairState) * h->max_frames));
+    DVO_CUDA(h, cudaMalloc(&h->chunk_sums, sizeof(float) * kMaxChunks * kChunkFloats * (size_t)h->max_frames));
 #ifdef DVO_BOUNDS_CHECK
     DVO_CUDA(h, cudaMalloc(&h->dbg_violations, sizeof(unsigned long long)));
     DVO_CUDA(h, cudaMemset(h->dbg_violations, 0, sizeof(unsigned long long)));
@@ -470,16 +491,19 @@ static void fill_params(const dvo_handle* h, AlignParams& p) {
         g.strips = h->lpitch[l] / kTile;
         g.n_tiles = g.strips * h->lh[l];
         g.h_magic = (unsigned)((1ull << 32) / (unsigned)h->lh[l]) + 1u;
-        {   // chunks per strip = NW * k with about 120 rows per chunk (align_kernel.cuh, fused_pass); measured per
-            // 2048 pairs: 30 / 60 / 120 / 240 rows -> 83.3 (60), 82.2 (120), 83.4 (240) ms
+        {   // chunks per strip = NW * k with about 60 rows per chunk (align_kernel.cuh, fused_pass).  The chunking fixes
+            // the summation order, so it depends on the image size and the launch shape only, never on the batch.
+            // Measured (profiles/r2/kernel_experiments.jsonl): 120-row chunks are 1 % faster on 4096 pairs, 60-row
+            // chunks 2.4 % faster on 512 pairs (the tail kernel's clusters of 32 warps get 40 chunks instead of 20).
             const int nw = h->threads / 32;
-            static const int target = [] {   // developer knob DVO_TUNE_CHUNK_ROWS (rows per chunk aimed at, default 120)
+            static const int target = [] {   // developer knob DVO_TUNE_CHUNK_ROWS (rows per chunk aimed at)
                 const char* e = getenv("DVO_TUNE_CHUNK_ROWS");
                 const int v = e ? atoi(e) : 0;
-                return (v >= 8 && v <= 2048) ? v : 120;
+                return (v >= 8 && v <= 2048) ? v : 60;
             }();
             int k = (h->lh[l] + nw * (target / 2)) / (nw * target);
             if (k < 1) k = 1;
+            while (k > 1 && nw * k * g.strips > kMaxChunks) --k;   // the chunk table holds kMaxChunks sums per level
             g.chunks_per_strip = nw * k;
             g.chunk_rows = (h->lh[l] + g.chunks_per_strip - 1) / g.chunks_per_strip;
         }
@@ -561,10 +585,31 @@ extern "C" int dvo_estimate(dvo_handle* h, int prev_base, int cur_base, int n_pa
     p.last_qt = last_qt_dev;
     p.out_qt = out_qt_dev;
     p.stats = stats_dev;
-    p.queue = h->queue + h->queue_next;
+    p.queue = h->queue + 8 * h->queue_next;
+    p.dlist = h->dlist + prev_base;
     h->queue_next = (h->queue_next + 1) % kQueueSlots;
-    DVO_CUDA(h, cudaMemsetAsync(p.queue, 0, sizeof(int), st));
+    p.ring = h->ring + prev_base;      // disjoint between launches in flight: they use disjoint frame slots
+    p.pstate = h->pstate + prev_base;
+    p.chunk_sums = h->chunk_sums + (size_t)prev_base * (kMaxChunks * kChunkFloats);
     const int grid = n_pairs < h->grid_max ? n_pairs : h->grid_max;
+    {   // time slice of the persistent kernel, in level-0 iterations (developer knob DVO_TUNE_QUANTUM, 0 = run every
+        // pair to completion); pointless when every pair has a CTA of its own
+        static const int q0 = [] {
+            const char* e = getenv("DVO_TUNE_QUANTUM");
+            const int v = e ? atoi(e) : 4;
+            return v < 0 ? 0 : v;
+        }();
+        p.quantum_tiles = (n_pairs > grid) ? q0 * p.lv[0].n_tiles : 0;
+    }
+    // tail kernel: clusters of `tail_c` CTAs finish the pairs still running when the persistent kernel's queue runs
+    // dry (developer knob DVO_TUNE_TAIL_CLUSTER: 0 = off, 2, 4 or 8)
+    static const int tail_c = [] {
+        const char* e = getenv("DVO_TUNE_TAIL_CLUSTER");
+        const int v = e ? atoi(e) : 4;
+        return (v == 2 || v == 4 || v == 8) ? v : 0;
+    }();
+    align_fn tfn = (p.quantum_tiles > 0 && tail_c > 0) ? get_tail(h) : nullptr;
+    p.defer = tfn ? 1 : 0;
     align_fn fn = get_align(h);
     align_fn cfn = h->cfg.cluster_size > 1 ? get_cluster(h) : nullptr;
     const int ev = (h->ev_last + 1) & 7;
@@ -587,7 +632,25 @@ extern "C" int dvo_estimate(dvo_handle* h, int prev_base, int cur_base, int n_pa
         lc.numAttrs = 1;
         DVO_CUDA(h, cudaLaunchKernelExC(&lc, (const void*)cfn, args));
     } else {
+        work_init_kernel<<<(n_pairs + 255) / 256, 256, 0, st>>>(p.queue, p.ring, p.pstate, n_pairs);
+        h->launches += 1;
         DVO_CUDA(h, cudaLaunchKernel((const void*)fn, dim3(grid), dim3(h->threads), args, 0, st));
+        if (tfn) {   // at most one deferred pair per CTA of the persistent grid
+            cudaLaunchConfig_t lc = {};
+            lc.gridDim = dim3((unsigned)grid * (unsigned)tail_c);
+            lc.blockDim = dim3(128);
+            lc.dynamicSmemBytes = 0;
+            lc.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)tail_c;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            lc.attrs = at;
+            lc.numAttrs = 1;
+            DVO_CUDA(h, cudaLaunchKernelExC(&lc, (const void*)tfn, args));
+            h->launches += 1;
+        }
     }
     DVO_CUDA(h, cudaEventRecord(h->ev1[ev], st));
     h->ev_last = ev;

@@ -86,6 +86,40 @@ static align_fn pick_cluster_variants(int w, int oob, int depth) {
 #endif
 }
 
+// Tail kernels (align_kernel with CL = 1: one thread-block cluster finishes one pair the persistent kernel left
+// unfinished), for one gradient mode; the same combinations as the cluster-mode kernels.
+template <int G>
+static align_fn pick_tail_variants(int w, int oob, int depth) {
+#ifdef DVO_FAST_BUILD
+    if (G == 0 && !depth && w == DVO_W_NONE && oob == DVO_OOB_INCLUSIVE)
+        return (align_fn)align_kernel<DVO_W_NONE, DVO_OOB_INCLUSIVE, G, 128, 2, 0, 1>;
+    return nullptr;
+#else
+    if (depth) {
+        if constexpr (G == 0) {
+#define DVO_PICKTD(WM, OM) \
+    if (w == WM && oob == OM) return (align_fn)align_kernel<WM, OM, 0, 128, 2, 1, 1>;
+            DVO_PICKTD(DVO_W_NONE, DVO_OOB_INCLUSIVE)
+            DVO_PICKTD(DVO_W_NONE, DVO_OOB_STRICT)
+            DVO_PICKTD(DVO_W_HUBER, DVO_OOB_INCLUSIVE)
+            DVO_PICKTD(DVO_W_HUBER, DVO_OOB_STRICT)
+#undef DVO_PICKTD
+        }
+        return nullptr;
+    }
+#define DVO_PICKT(WM, OM) \
+    if (w == WM && oob == OM) return (align_fn)align_kernel<WM, OM, G, 128, 2, 0, 1>;
+    DVO_PICKT(DVO_W_NONE, DVO_OOB_INCLUSIVE)
+    DVO_PICKT(DVO_W_NONE, DVO_OOB_STRICT)
+    DVO_PICKT(DVO_W_HUBER, DVO_OOB_INCLUSIVE)
+    DVO_PICKT(DVO_W_HUBER, DVO_OOB_STRICT)
+    DVO_PICKT(DVO_W_TDIST_REF, DVO_OOB_INCLUSIVE)
+    DVO_PICKT(DVO_W_TDIST_REF, DVO_OOB_STRICT)
+#undef DVO_PICKT
+    return nullptr;
+#endif
+}
+
 // one definition per variants_*.cu
 align_fn pick_align_128_g0(int w, int oob, int depth);
 align_fn pick_align_128_g1(int w, int oob);
@@ -93,5 +127,7 @@ align_fn pick_align_256_g0(int w, int oob, int depth);
 align_fn pick_align_256_g1(int w, int oob);
 align_fn pick_cluster_g0(int w, int oob, int depth);
 align_fn pick_cluster_g1(int w, int oob);
+align_fn pick_tail_g0(int w, int oob, int depth);
+align_fn pick_tail_g1(int w, int oob);
 
 }  // namespace dvo
