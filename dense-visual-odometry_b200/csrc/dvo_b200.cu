@@ -605,7 +605,7 @@ extern "C" int dvo_estimate(dvo_handle* h, int prev_base, int cur_base, int n_pa
     // dry (developer knob DVO_TUNE_TAIL_CLUSTER: 0 = off, 2, 4 or 8)
     static const int tail_c = [] {
         const char* e = getenv("DVO_TUNE_TAIL_CLUSTER");
-        const int v = e ? atoi(e) : 4;
+        const int v = e ? atoi(e) : 8;
         return (v == 2 || v == 4 || v == 8) ? v : 0;
     }();
     align_fn tfn = (p.quantum_tiles > 0 && tail_c > 0) ? get_tail(h) : nullptr;

@@ -15,10 +15,13 @@ cam = m.RGBDCameraModel(Km, TUM_DEPTH_SCALE)
 dev = torch.device("cuda", 0)
 args = [torch.as_tensor(d[k]).to(dev) for k in ("bgr_prev", "depth_prev", "bgr_cur", "depth_cur")]
 ref = None
+W = dict(weights=sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1] != "depth" else {}
+if len(sys.argv) > 1 and sys.argv[1] == "depth":
+    W = dict(use_depth_residual=True)
 for name, kw in [("1 CTA x 128 thr", dict(threads_per_block=128)), ("1 CTA x 256 thr", dict(threads_per_block=256)),
                  ("cluster 2", dict(cluster_size=2)), ("cluster 4", dict(cluster_size=4)),
                  ("cluster 8", dict(cluster_size=8)), ("cluster 16", dict(cluster_size=16))]:
-    al = m.PairBatchAligner(cam, 480, 640, 4, max_pairs=1, **kw)
+    al = m.PairBatchAligner(cam, 480, 640, 4, max_pairs=1, **kw, **W)
     al.build(*args)
     for _ in range(3):
         qt, st = al.estimate()
