@@ -574,6 +574,10 @@ class SequenceAligner:
             bgr = (torch.as_tensor(bgr) if isinstance(bgr, np.ndarray) else bgr).contiguous()
             depth = (torch.as_tensor(depth) if isinstance(depth, np.ndarray) else depth).contiguous()
             self._keep = (bgr, depth)
+        else:
+            # nothing to overlap with: one launch for all pairs, so that the kernel's work queue balances them over
+            # the SMs and its tail kernel finishes the last ones (chunks exist to hide the upload of host frames)
+            chunk_frames = N
         cur = torch.cuda.current_stream(self._dev)
         cs = self._copy_stream
         cs.wait_stream(cur)
