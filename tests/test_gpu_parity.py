@@ -5,6 +5,7 @@ REAL reference (tests/golden/).  Tolerances follow BASELINE.json's north_star:
   max magnitude); final pose: 1e-4 rad / 1e-4 m."""
 import hashlib
 import json
+import os
 
 import numpy as np
 import pytest
@@ -113,6 +114,15 @@ def _compare_level(est, m, ld, pose, lv, oob, report):
     Js = float(np.abs(Jd[both]).max())
     report[f"L{lv}_r_rel"] = float(dr.max() / rs)
     report[f"L{lv}_J_rel"] = float(dJ.max() / Js)
+    # the distribution behind the two maxima (relative to the plane's largest magnitude), and element-wise relative
+    # differences of the Jacobian entries that are not tiny
+    pct = [50, 90, 99, 99.9, 100]
+    big = np.abs(Jd[both]) > 1e-3 * Js
+    report.setdefault("percentiles", pct)
+    report.setdefault(f"L{lv}_r_rel_pct", []).append([float(v) for v in np.percentile(dr / rs, pct)])
+    report.setdefault(f"L{lv}_J_rel_pct", []).append([float(v) for v in np.percentile(dJ / Js, pct)])
+    report.setdefault(f"L{lv}_J_elementwise_rel_pct", []).append(
+        [float(v) for v in np.percentile(dJ[big] / np.abs(Jd[both])[big], pct)])
     assert dr.max() <= 1e-5 * rs, f"residuals differ by {dr.max()} (scale {rs})"
     assert dJ.max() <= 1e-5 * Js, f"Jacobians differ by {dJ.max()} (scale {Js})"
     # fused reduction of the same pass against float64 sums of the oracle's r, J
@@ -147,6 +157,11 @@ def test_residuals_jacobian_dense_vs_oracle(dvo_mod, testdata_frames, oob):
         for pose in poses:
             _compare_level(est, m, ld, pose, lv, O.OOB_STRICT if oob == "strict" else O.OOB_INCLUSIVE, report)
     print("dense parity:", report)
+    out = os.environ.get("DVO_PARITY_REPORT")
+    if out:   # committed once per round under profiles/ (one list entry per tested pose, identity first)
+        import json
+        with open(f"{out}_{oob}.json", "w") as f:
+            json.dump(report, f, indent=1)
 
 
 @pytest.mark.parametrize("pair,variant", [(1, ""), (4, ""), (1, "_strict")])
