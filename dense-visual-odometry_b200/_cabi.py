@@ -60,6 +60,7 @@ SYMBOLS = {
     "dvo_residuals_jacobian": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P]),
     "dvo_depth_residuals_jacobian": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
     "dvo_get_pyramid": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
+    "dvo_get_point_list": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
     "dvo_level_shape": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "dvo_level_intrinsics": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float)]),
     "dvo_launch_count": (C.c_longlong, [_P]),

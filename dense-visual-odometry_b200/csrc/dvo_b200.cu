@@ -31,7 +31,8 @@ struct dvo_handle {
     uint8_t* gray[DVO_MAX_LEVELS]{};
     uint16_t* depth[DVO_MAX_LEVELS]{};
     uint2* rec[DVO_MAX_LEVELS]{};
-    float* prec[DVO_MAX_LEVELS]{};   // previous-frame planes: z and -(0.5 + I/512), 2 floats per pixel (align_kernel.cuh, prec_index)
+    float* prec[DVO_MAX_LEVELS]{};   // previous-frame point lists, room for 2 words per pixel (align_kernel.cuh, pt_pack)
+    int* pt_tiles[DVO_MAX_LEVELS]{};   // [frame] tiles of the frame's point list
     float k4[DVO_MAX_LEVELS][4]{}, kinv4[DVO_MAX_LEVELS][4]{};
     int* queue = nullptr;   // kQueueSlots x 4 work-queue counters; concurrent dvo_estimate calls (different streams) rotate through them
     int queue_next = 0;
@@ -153,6 +154,7 @@ extern "C" int dvo_destroy(dvo_handle* h) {
         cudaFree(h->depth[l]);
         cudaFree(h->rec[l]);
         cudaFree(h->prec[l]);
+        cudaFree(h->pt_tiles[l]);
     }
     cudaFree(h->queue);
     cudaFree(h->ring);
@@ -182,6 +184,10 @@ static int create_impl(dvo_handle* h) {
     h->sm_count = prop.multiProcessorCount;
     if (h->cfg.reserved[0] > kMaxPrefetchRows) {   // the kernels read that many rows ahead; the plane slack is sized for it
         h->err = "reserved[0] (L1 prefetch distance in rows) must be <= 32";
+        return DVO_ERR_INVALID;
+    }
+    if (h->W > kPtMaxDim + 1 || h->H > kPtMaxDim + 1) {   // a point word holds 11-bit column and row indices (pt_pack)
+        h->err = "image too large: width and height must be <= 2048";
         return DVO_ERR_INVALID;
     }
     int w = h->W, hh = h->H;
@@ -214,7 +220,9 @@ static int create_impl(dvo_handle* h) {
         DVO_CUDA(h, cudaMemset(h->depth[l], 0, n_raw * sizeof(uint16_t)));
         DVO_CUDA(h, cudaMemset(h->rec[l], 0, n_rec * sizeof(uint2)));
         DVO_CUDA(h, cudaMalloc(&h->prec[l], 2 * n_raw * sizeof(float)));
-        prec_fill_kernel<<<h->sm_count * 8, 256>>>(h->prec[l], 2 * n_raw);   // "no depth" everywhere, padding keeps it
+        prec_fill_kernel<<<h->sm_count * 8, 256>>>(h->prec[l], 2 * n_raw);   // "no depth" points everywhere
+        DVO_CUDA(h, cudaMalloc(&h->pt_tiles[l], (size_t)h->max_frames * sizeof(int)));
+        DVO_CUDA(h, cudaMemset(h->pt_tiles[l], 0, (size_t)h->max_frames * sizeof(int)));
         DVO_CUDA(h, cudaGetLastError());
         {   // strip = umulhi(t, floor(2^32/h)+1) must be exact for every tile index of the plane
             const unsigned magic = (unsigned)((1ull << 32) / (unsigned)hh) + 1u;
@@ -351,16 +359,24 @@ extern "C" long long dvo_launch_count(const dvo_handle* h) { return h ? h->launc
 // with_gradients (the `roles` of the frames): 0 = used as previous frames only (previous-frame records, no tap
 // records), 1 = both roles, 2 = used as current frames only (tap records, no previous-frame records).
 static int build_levels(dvo_handle* h, int frame_base, int n_frames, int with_gradients, cudaStream_t st) {
-    const bool want_prec = with_gradients != 2;
     for (int l = 1; l < h->levels; ++l) {
         const int groups = (h->lw[l] + 3) / 4 * h->lh[l];
         dim3 grid((groups + 127) / 128, n_frames);
         median3_down_pair_kernel<<<grid, 128, 0, st>>>(
             h->gray[l - 1] + (size_t)frame_base * h->lplane[l - 1], h->gray[l] + (size_t)frame_base * h->lplane[l],
             h->depth[l - 1] + (size_t)frame_base * h->lplane[l - 1], h->depth[l] + (size_t)frame_base * h->lplane[l],
-            want_prec ? h->prec[l] + 2 * (size_t)frame_base * h->lplane[l] : nullptr, h->depth_scale, h->lw[l - 1], h->lh[l - 1], h->lpitch[l - 1], h->lplane[l - 1], h->lw[l], h->lh[l], h->lpitch[l],
-            h->lplane[l]);
+            h->lw[l - 1], h->lh[l - 1], h->lpitch[l - 1], h->lplane[l - 1], h->lw[l], h->lh[l], h->lpitch[l], h->lplane[l]);
         h->launches += 1;
+    }
+    if (with_gradients != 2) {   // frames used as previous frames: their point lists
+        for (int l = 0; l < h->levels; ++l) {
+            points_kernel<<<n_frames, 1024, 0, st>>>(h->gray[l] + (size_t)frame_base * h->lplane[l],
+                                                     h->depth[l] + (size_t)frame_base * h->lplane[l],
+                                                     h->prec[l] + 2 * (size_t)frame_base * h->lplane[l],
+                                                     h->pt_tiles[l] + frame_base, h->depth_scale, h->lw[l], h->lh[l],
+                                                     h->lpitch[l], h->lplane[l]);
+            h->launches += 1;
+        }
     }
     if (with_gradients) {
         for (int l = 0; l < h->levels; ++l) {
@@ -391,10 +407,9 @@ static int build_impl(dvo_handle* h, int frame_base, const uint8_t* img, uint16_
     const bool vec = (h->W % 4 == 0) && (((uintptr_t)img & 3) == 0) && (((uintptr_t)depth & 7) == 0);
     uint8_t* g0 = h->gray[0] + (size_t)frame_base * h->lplane[0];
     uint16_t* d0 = h->depth[0] + (size_t)frame_base * h->lplane[0];
-    float* p0 = with_gradients != 2 ? h->prec[0] + 2 * (size_t)frame_base * h->lplane[0] : nullptr;
-#define DVO_LAUNCH_GC(V, B)                                                                                        \
-    gray_clamp_kernel<V, B><<<grid, 256, 0, st>>>(img, depth, g0, d0, p0, h->depth_scale, h->W, h->H, h->lpitch[0], \
-                                                  h->lplane[0], h->clamp_thr, clamp ? 1 : 0)
+#define DVO_LAUNCH_GC(V, B)                                                                                  \
+    gray_clamp_kernel<V, B><<<grid, 256, 0, st>>>(img, depth, g0, d0, h->W, h->H, h->lpitch[0], h->lplane[0], \
+                                                  h->clamp_thr, clamp ? 1 : 0)
     if (vec && has_bgr) DVO_LAUNCH_GC(true, true);
     else if (vec) DVO_LAUNCH_GC(true, false);
     else if (has_bgr) DVO_LAUNCH_GC(false, true);
@@ -475,6 +490,23 @@ extern "C" int dvo_get_pyramid(dvo_handle* h, int slot, int level, uint8_t* gray
     return DVO_OK;
 }
 
+extern "C" int dvo_get_point_list(dvo_handle* h, int slot, int level, float* z_dev, int* col_dev, int* row_dev,
+                                  uint8_t* intensity_dev, int* n_dev, void* stream) {
+    if (!h) return DVO_ERR_INVALID;
+    if (slot < 0 || slot >= h->max_frames || level < 0 || level >= h->levels)
+        return fail(h, DVO_ERR_RANGE, "slot / level out of range");
+    DVO_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int cap = h->lw[level] * h->lh[level];
+    if (n_dev) DVO_CUDA(h, cudaMemsetAsync(n_dev, 0, 2 * sizeof(int), st));
+    point_list_dump_kernel<<<(cap + 127 + 255) / 256, 256, 0, st>>>(h->prec[level] + 2 * (size_t)slot * h->lplane[level],
+                                                                    h->pt_tiles[level] + slot, z_dev, col_dev, row_dev,
+                                                                    intensity_dev, n_dev, cap);
+    h->launches += 1;
+    DVO_CUDA(h, cudaGetLastError());
+    return DVO_OK;
+}
+
 // ---- estimate ----------------------------------------------------------------------------------
 static void fill_params(const dvo_handle* h, AlignParams& p) {
     memset(&p, 0, sizeof(p));
@@ -484,6 +516,7 @@ static void fill_params(const dvo_handle* h, AlignParams& p) {
         g.depth = h->depth[l];
         g.rec = h->rec[l];
         g.prec = h->prec[l];
+        g.pt_tiles = h->pt_tiles[l];
         g.plane = h->lplane[l];
         g.w = h->lw[l];
         g.h = h->lh[l];
@@ -491,21 +524,21 @@ static void fill_params(const dvo_handle* h, AlignParams& p) {
         g.strips = h->lpitch[l] / kTile;
         g.n_tiles = g.strips * h->lh[l];
         g.h_magic = (unsigned)((1ull << 32) / (unsigned)h->lh[l]) + 1u;
-        {   // chunks per strip = NW * k with about 60 rows per chunk (align_kernel.cuh, fused_pass).  The chunking fixes
-            // the summation order, so it depends on the image size and the launch shape only, never on the batch.
-            // Measured (profiles/r2/kernel_experiments.jsonl): 120-row chunks are 1 % faster on 4096 pairs, 60-row
-            // chunks 2.4 % faster on 512 pairs (the tail kernel's clusters of 32 warps get 40 chunks instead of 20).
+        {   // n_chunks = NW * k with about 60 tiles per chunk of a full point list (align_kernel.cuh, fused_pass).  The
+            // chunking fixes the summation order, so it depends on the image size and the launch shape only, never on
+            // the batch.  Measured (profiles/r2/kernel_experiments.jsonl): 120-tile chunks are 1 % faster on 4096 pairs,
+            // 60-tile chunks 2.4 % faster on 512 pairs (the tail kernel's clusters of 32 warps get 40 chunks, not 20).
             const int nw = h->threads / 32;
-            static const int target = [] {   // developer knob DVO_TUNE_CHUNK_ROWS (rows per chunk aimed at)
+            static const int target = [] {   // developer knob DVO_TUNE_CHUNK_ROWS (tiles per chunk aimed at)
                 const char* e = getenv("DVO_TUNE_CHUNK_ROWS");
                 const int v = e ? atoi(e) : 0;
                 return (v >= 8 && v <= 2048) ? v : 60;
             }();
-            int k = (h->lh[l] + nw * (target / 2)) / (nw * target);
+            const int dense_tiles = (h->lw[l] * h->lh[l] + kTile - 1) / kTile;
+            int k = (dense_tiles + nw * (target / 2)) / (nw * target);
             if (k < 1) k = 1;
-            while (k > 1 && nw * k * g.strips > kMaxChunks) --k;   // the chunk table holds kMaxChunks sums per level
-            g.chunks_per_strip = nw * k;
-            g.chunk_rows = (h->lh[l] + g.chunks_per_strip - 1) / g.chunks_per_strip;
+            while (k > 1 && nw * k > kMaxChunks) --k;   // the chunk table holds kMaxChunks sums per level
+            g.n_chunks = nw * k;
         }
 #ifdef DVO_BOUNDS_CHECK
         p.dbg_rec_lo[l] = reinterpret_cast<const char*>(h->rec[l]);
@@ -522,6 +555,7 @@ static void fill_params(const dvo_handle* h, AlignParams& p) {
         g.ifx = h->kinv4[l][0]; g.ify = h->kinv4[l][1]; g.icx = h->kinv4[l][2]; g.icy = h->kinv4[l][3];
     }
     p.levels = h->levels;
+    p.depth_scale = h->depth_scale;
     p.max_iterations = h->cfg.max_iterations;
     p.max_increased_steps = h->cfg.max_increased_steps;
     p.tolerance = h->cfg.tolerance;
@@ -539,6 +573,12 @@ static void fill_params(const dvo_handle* h, AlignParams& p) {
     // tuning knob (dvo_config.reserved[0]): L1 prefetch distance in rows; 0 = default (2), < 0 = off
     p.prefetch_rows = h->cfg.reserved[0] > 0 ? h->cfg.reserved[0] : (h->cfg.reserved[0] < 0 ? 0 : 2);
     p.prefetch_raw_rows = p.prefetch_rows;
+    {   // developer knobs DVO_TUNE_PF (tap rows ahead) / DVO_TUNE_RAW_PF (point-list tiles ahead), 1..32
+        static const int pf = [] { const char* e = getenv("DVO_TUNE_PF"); return e ? atoi(e) : 0; }();
+        static const int raw = [] { const char* e = getenv("DVO_TUNE_RAW_PF"); return e ? atoi(e) : 0; }();
+        if (pf >= 1 && pf <= 32 && p.prefetch_rows > 0) p.prefetch_rows = pf;
+        if (raw >= 1 && raw <= 32 && p.prefetch_rows > 0) p.prefetch_raw_rows = raw;
+    }
     {   // residual-only passes run further ahead; developer knob DVO_TUNE_RES_PF (rows, 1..32)
         static const int res_rows = [] {
             const char* e = getenv("DVO_TUNE_RES_PF");

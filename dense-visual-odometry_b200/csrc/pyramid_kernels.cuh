@@ -4,15 +4,16 @@
 //                         (reference: core/base_dense_visual_odometry.py:58-59)
 //   median3_down_pair_kernel  3x3 median, replicated border, keep even rows/cols (gray and depth level in one launch)
 //                         (reference: utils/image_pyramid.py:19-21, cv2.medianBlur(.,3)[::2, ::2])
-//                         both also write the level's previous-frame planes z, -(0.5 + I/512) (prec_store in
-//                         align_kernel.cuh: camera_model.py:199-200 hoisted out of the Gauss-Newton loop)
+//   points_kernel         the level's pixels with depth, compacted into the previous-frame POINT LIST the alignment
+//                         kernel walks (pt_pack in align_kernel.cuh; camera_model.py:171-226: the masked point cloud,
+//                         with z = fl32(float64(d) * scale) of :199-200 hoisted out of the Gauss-Newton loop)
 //   sobel3_kernel         3x3 Sobel dx/dy, gain 8, replicated border -> packed 8-byte records {gx, gy, I, depth}
 //                         (reference: utils/jacobian.py:70-71; layout: rec_pack in align_kernel.cuh); the
 //                         intensity rides along so that one 8-byte load per bilinear tap feeds the alignment kernel
 //
 // Plane layout: every level plane is [frame][h][pitch] with pitch a multiple of 16 elements; padding
 // columns stay as initialised at creation (kernels only write col < w): zero in the gray / depth / tap-record
-// planes, "no depth" (z = +inf) in the previous-frame record planes.
+// planes.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -25,9 +26,8 @@ namespace dvo {
 template <bool VEC, bool HAS_BGR>
 __global__ void __launch_bounds__(256) gray_clamp_kernel(const uint8_t* __restrict__ bgr_or_gray,
                                                          uint16_t* __restrict__ depth_io, uint8_t* __restrict__ gray0,
-                                                         uint16_t* __restrict__ depth0, float* __restrict__ prec0,
-                                                         double depth_scale, int w, int h, int pitch, size_t plane,
-                                                         int clamp_thr, int do_clamp) {
+                                                         uint16_t* __restrict__ depth0, int w, int h, int pitch,
+                                                         size_t plane, int clamp_thr, int do_clamp) {
     const int gpr = (w + 3) >> 2;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int frame = blockIdx.y;
@@ -86,11 +86,6 @@ __global__ void __launch_bounds__(256) gray_clamp_kernel(const uint8_t* __restri
         *reinterpret_cast<uchar4*>(gray0 + out) = make_uchar4(gr[0], gr[1], gr[2], gr[3]);
         *reinterpret_cast<ushort4*>(depth0 + out) = make_ushort4(d[0], d[1], d[2], d[3]);
         if (changed) *reinterpret_cast<ushort4*>(depth_io + in_px) = make_ushort4(d[0], d[1], d[2], d[3]);
-        if (prec0) {
-            float* prow = prec0 + 2u * ((size_t)frame * plane + (size_t)row * pitch);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) prec_store(prow, col + k, d[k], gr[k], depth_scale);
-        }
     } else {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -98,17 +93,83 @@ __global__ void __launch_bounds__(256) gray_clamp_kernel(const uint8_t* __restri
                 gray0[out + k] = gr[k];
                 depth0[out + k] = d[k];
                 if (changed) depth_io[in_px + k] = d[k];
-                if (prec0)
-                    prec_store(prec0 + 2u * ((size_t)frame * plane + (size_t)row * pitch), col + k, d[k], gr[k], depth_scale);
             }
     }
 }
 
-// Initial state of a previous-frame record plane: "no depth" everywhere (the padding columns keep it).
+// Initial state of a point-list buffer: "no depth" points everywhere (tiles of 128 z values, 128 point words).
 __global__ void prec_fill_kernel(float* __restrict__ p, size_t n_floats) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_floats; i += stride)
-        p[i] = __uint_as_float(((i >> 7) & 1) ? kPrecNoIntensity : kPrecNoDepth);   // 128 z values, 128 c values, ...
+        p[i] = __uint_as_float(((i >> 7) & 1) ? 0u : kPrecNoDepth);
+}
+
+// ---- a4 -----------------------------------------------------------------------------------------
+// The point list of one level of every frame (layout and order: align_kernel.cuh, "previous-frame point lists").
+// One CTA of 32 warps per frame walks the level strip by strip, 32 rows at a time: warp = row, lane = four columns
+// of the strip's 128; a block-wide exclusive scan of the per-thread counts gives every point its place in the list
+// (one __syncthreads per step: the warp totals alternate between two shared buffers).  The last tile is padded with
+// "no depth" points; pt_tiles[frame] receives the number of tiles.
+__global__ void __launch_bounds__(1024) points_kernel(const uint8_t* __restrict__ gray, const uint16_t* __restrict__ depth,
+                                                      float* __restrict__ list, int* __restrict__ pt_tiles,
+                                                      double depth_scale, int w, int h, int pitch, size_t plane) {
+    __shared__ int s_tot[2][32];
+    const int frame = blockIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint8_t* g8 = gray + (size_t)frame * plane;
+    const uint16_t* d16 = depth + (size_t)frame * plane;
+    float* out = list + 2u * (size_t)frame * plane;
+    const int strips = (w + 127) >> 7;
+    int base = 0, buf = 0;
+    for (int s = 0; s < strips; ++s) {
+        const int col = s * 128 + 4 * lane;
+        for (int r0 = 0; r0 < h; r0 += 32) {
+            const int row = r0 + wid;
+            unsigned dd[4] = {0u, 0u, 0u, 0u};
+            unsigned gw = 0u;
+            if (row < h) {   // the padding columns of the depth plane are zero: no depth
+                const size_t e = (size_t)row * pitch + col;
+                const uint2 dv = __ldg(reinterpret_cast<const uint2*>(d16 + e));
+                gw = __ldg(reinterpret_cast<const unsigned*>(g8 + e));
+                dd[0] = dv.x & 0xffffu; dd[1] = dv.x >> 16; dd[2] = dv.y & 0xffffu; dd[3] = dv.y >> 16;
+            }
+            const int cnt = (dd[0] != 0u) + (dd[1] != 0u) + (dd[2] != 0u) + (dd[3] != 0u);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (lane == 31) s_tot[buf][wid] = incl;
+            __syncthreads();
+            int wincl = s_tot[buf][lane];   // inclusive scan of the 32 warp totals, in every warp
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, wincl, o);
+                if (lane >= o) wincl += v;
+            }
+            const int before = __shfl_sync(0xffffffffu, wincl, (wid + 31) & 31);
+            const int total = __shfl_sync(0xffffffffu, wincl, 31);
+            int pos = base + (wid ? before : 0) + incl - cnt;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (dd[k] != 0u) {
+                    float* t = out + (size_t)(pos >> 7) * 256u + pt_index(pos & 127);
+                    t[0] = (float)((double)dd[k] * depth_scale);
+                    t[128] = __uint_as_float(pt_pack(col + k, row, (gw >> (8 * k)) & 255u));
+                    ++pos;
+                }
+            base += total;
+            buf ^= 1;
+        }
+    }
+    const int n_tiles = (base + 127) >> 7;
+    for (int pos = base + (int)threadIdx.x; pos < n_tiles * 128; pos += 1024) {
+        float* t = out + (size_t)(pos >> 7) * 256u + pt_index(pos & 127);
+        t[0] = __uint_as_float(kPrecNoDepth);
+        t[128] = 0.0f;
+    }
+    if (threadIdx.x == 0) pt_tiles[frame] = n_tiles;
 }
 
 // ---- a2 -----------------------------------------------------------------------------------------
@@ -163,8 +224,7 @@ __device__ __forceinline__ void load_row9(const T* __restrict__ row, int k, int 
 // (one block per row left 37-84 % of the threads idle there).
 __global__ void __launch_bounds__(128) median3_down_pair_kernel(const uint8_t* __restrict__ src8, uint8_t* __restrict__ dst8,
                                                                 const uint16_t* __restrict__ src16,
-                                                                uint16_t* __restrict__ dst16, float* __restrict__ dprec,
-                                                                double depth_scale, int sw, int sh, int spitch,
+                                                                uint16_t* __restrict__ dst16, int sw, int sh, int spitch,
                                                                 size_t splane, int dw, int dh, int dpitch, size_t dplane) {
     const int kpr = (dw + 3) >> 2;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -198,18 +258,10 @@ __global__ void __launch_bounds__(128) median3_down_pair_kernel(const uint8_t* _
             (uint32_t)m[0] | ((uint32_t)m[1] << 8) | ((uint32_t)m[2] << 16) | ((uint32_t)m[3] << 24);
         *reinterpret_cast<uint2*>(dst16 + o) =
             make_uint2((uint32_t)n[0] | ((uint32_t)n[1] << 16), (uint32_t)n[2] | ((uint32_t)n[3] << 16));
-        if (dprec) {
-            float* prow = dprec + 2u * ((size_t)frame * dplane + (size_t)oy * dpitch);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) prec_store(prow, ox + j, (unsigned)n[j], (unsigned)m[j], depth_scale);
-        }
     } else {
         for (int j = 0; j < 4 && ox + j < dw; ++j) {   // padding columns keep their initial state
             dst8[o + j] = (uint8_t)m[j];
             dst16[o + j] = (uint16_t)n[j];
-            if (dprec)
-                prec_store(dprec + 2u * ((size_t)frame * dplane + (size_t)oy * dpitch), ox + j, (unsigned)n[j], (unsigned)m[j],
-                           depth_scale);
         }
     }
 }
@@ -280,6 +332,26 @@ __global__ void unpitch_grad_kernel(const uint2* __restrict__ src, float* __rest
         if (gx) gx[(size_t)y * w + x] = (float)a;
         if (gy) gy[(size_t)y * w + x] = (float)b;
     }
+}
+
+// Read-back of one point list in list order (dvo_get_point_list); the padding of the last tile is dropped.
+__global__ void point_list_dump_kernel(const float* __restrict__ list, const int* __restrict__ pt_tiles,
+                                       float* __restrict__ z_out, int* __restrict__ col_out, int* __restrict__ row_out,
+                                       uint8_t* __restrict__ i_out, int* __restrict__ n_out, int capacity) {
+    const int n_tiles = *pt_tiles;
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos == 0 && n_out) n_out[1] = n_tiles;
+    if (pos >= n_tiles * 128) return;
+    const float* t = list + (size_t)(pos >> 7) * 256u + pt_index(pos & 127);
+    const float z = t[0];
+    if (__float_as_uint(z) == kPrecNoDepth) return;   // padding (only at the end of the list)
+    if (n_out) atomicAdd(n_out, 1);
+    if (pos >= capacity) return;
+    const unsigned w = __float_as_uint(t[128]);
+    if (z_out) z_out[pos] = z;
+    if (col_out) col_out[pos] = pt_col(w);
+    if (row_out) row_out[pos] = pt_row(w);
+    if (i_out) i_out[pos] = (uint8_t)((w >> 11) & 255u);
 }
 
 }  // namespace dvo

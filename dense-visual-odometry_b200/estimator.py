@@ -387,6 +387,24 @@ class RobustDVOB200:
         return g.cpu().numpy(), d.cpu().numpy(), gx.cpu().numpy(), gy.cpu().numpy()
 
 
+    def get_point_list(self, slot: int, level: int):
+        """(z f32, col i32, row i32, intensity u8) of the frame slot's point list at one level, in list order: the
+        pixels with depth, as the alignment kernel walks them when the frame is the previous frame of a pair."""
+        torch = self._torch
+        hl, wl = self._h.level_shape(level)
+        st = _stream_ptr(torch, self._dev)
+        z = torch.empty(hl * wl, dtype=torch.float32, device=self._dev)
+        col = torch.empty(hl * wl, dtype=torch.int32, device=self._dev)
+        row = torch.empty(hl * wl, dtype=torch.int32, device=self._dev)
+        inten = torch.empty(hl * wl, dtype=torch.uint8, device=self._dev)
+        n = torch.zeros(2, dtype=torch.int32, device=self._dev)
+        self._h.call("dvo_get_point_list", slot, level, C.c_void_p(z.data_ptr()), C.c_void_p(col.data_ptr()),
+                     C.c_void_p(row.data_ptr()), C.c_void_p(inten.data_ptr()), C.c_void_p(n.data_ptr()), st)
+        torch.cuda.current_stream(self._dev).synchronize()
+        k = int(n[0].item())
+        return z[:k].cpu().numpy(), col[:k].cpu().numpy(), row[:k].cpu().numpy(), inten[:k].cpu().numpy()
+
+
 class PairBatchAligner:
     """B independent frame pairs per call (BASELINE.json configs 2-4): one persistent kernel launch runs
     every pair's coarse-to-fine Gauss-Newton on the device.

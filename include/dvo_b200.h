@@ -183,6 +183,13 @@ int dvo_depth_residuals_jacobian(dvo_handle* h, int prev_slot, int cur_slot, int
 int dvo_get_pyramid(dvo_handle* h, int slot, int level, uint8_t* gray_dev, uint16_t* depth_dev, float* gx_dev,
                     float* gy_dev, void* stream);
 int dvo_level_shape(const dvo_handle* h, int level, int* height, int* width);
+/* Reads back the point list of one level of a frame slot built with with_gradients 0 or 1: the pixels with depth, the
+ * form in which the alignment kernel consumes a PREVIOUS frame (the masked point cloud of RGBDCameraModel.deproject,
+ * camera_model.py:171-226, with z = fl32(float64(d) * depth_scale) of :199-200).  Order: 128-pixel-wide column strips
+ * left to right, row-major inside a strip.  z_dev f32, col_dev / row_dev i32, intensity_dev u8: [H_l*W_l] each, the
+ * first n entries are written (any may be NULL); n_dev i32[2] = {n = number of points, number of 128-point tiles}. */
+int dvo_get_point_list(dvo_handle* h, int slot, int level, float* z_dev, int* col_dev, int* row_dev,
+                       uint8_t* intensity_dev, int* n_dev, void* stream);
 /* Per-level intrinsics fx, fy, cx, cy as the kernels use them (camera_model.py:62-79). */
 int dvo_level_intrinsics(const dvo_handle* h, int level, float* k4);
 

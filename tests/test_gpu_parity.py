@@ -72,6 +72,53 @@ def test_pyramids_odd_size(dvo_mod, golden_dir):
         assert _dg(gx) == prim[f"odd_gx_L{lv}"] and _dg(gy) == prim[f"odd_gy_L{lv}"]
 
 
+# ------------------------------------------------------------------------------------------------ a4
+def _expected_point_list(gray, depth, depth_scale):
+    """Pixels with depth, 128-pixel-wide column strips left to right, row-major inside a strip; z as
+    camera_model.py:199-200 rounds it (float64 product -> float32)."""
+    h, w = depth.shape
+    z, col, row, inten = [], [], [], []
+    for s in range(0, w, 128):
+        rr, cc = np.nonzero(depth[:, s:s + 128])
+        cc = cc + s
+        z.append((depth[rr, cc].astype(np.float64) * depth_scale).astype(np.float32))
+        col.append(cc)
+        row.append(rr)
+        inten.append(gray[rr, cc])
+    return np.concatenate(z), np.concatenate(col), np.concatenate(row), np.concatenate(inten)
+
+
+def test_point_list_bit_exact(dvo_mod, testdata_frames):
+    """The previous-frame point list (the masked point cloud of RGBDCameraModel.deproject) of every level: the test
+    frames (a quarter of the pixels without depth), an odd size with a partial last strip, a frame with no depth at
+    all and a frame with depth everywhere."""
+    f = testdata_frames
+    est = _estimator(dvo_mod, f["K"], f["depth_scale"], 4)
+    est.step(f["bgr"][0], f["depth"][0].copy())
+    gp = O.build_pyramid(O.bgr_to_gray(f["bgr"][0]), 4)
+    dp = O.build_pyramid(O.clamp_depth(f["depth"][0], f["depth_scale"]), 4)
+    for lv in range(4):
+        got = est.get_point_list(est._prev_slot, lv)
+        want = _expected_point_list(gp[lv], dp[lv], f["depth_scale"])
+        assert len(got[0]) == int((dp[lv] != 0).sum())
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b)
+    rng = np.random.default_rng(11)
+    for hh, ww, frac in ((77, 301, 0.3), (64, 130, 1.0), (50, 128, 0.0)):
+        g8 = rng.integers(0, 256, (hh, ww), dtype=np.uint8)
+        d16 = rng.integers(1, 65536, (hh, ww), dtype=np.uint16)
+        d16[rng.random((hh, ww)) < frac] = 0
+        est = _estimator(dvo_mod, (100.0, 100.0, ww / 2, hh / 2), 1e-9, 3)   # scale so small that nothing is clamped
+        est.step(np.repeat(g8[..., None], 3, -1), d16.copy())
+        gp, dp = O.build_pyramid(g8, 3), O.build_pyramid(d16, 3)
+        for lv in range(3):
+            got = est.get_point_list(est._prev_slot, lv)
+            want = _expected_point_list(gp[lv], dp[lv], 1e-9)
+            assert len(got[0]) == int((dp[lv] != 0).sum())
+            for a, b in zip(got, want):
+                assert np.array_equal(a, b)
+
+
 def test_gray_conversion_lattice(dvo_mod, golden_dir):
     prim = json.loads((golden_dir / "primitives.json").read_text())
     rng = np.random.default_rng(7)
