@@ -248,6 +248,14 @@ static int create_impl(dvo_handle* h) {
         h->err = "cluster_size must be 0, 1, 2, 4, 8 or 16";
         return DVO_ERR_INVALID;
     }
+    {   // points_kernel keeps one count per (strip, row) of a level in shared memory
+        const size_t smem = points_smem_bytes(h->lpitch[0] / kTile, h->lh[0]);
+        if (smem > 200 * 1024) {
+            h->err = "image too large for the point-list build (strips x rows of level 0 must fit shared memory)";
+            return DVO_ERR_INVALID;
+        }
+        DVO_CUDA(h, cudaFuncSetAttribute((const void*)points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     align_fn fn = get_align(h);
     if (!fn) {
         h->err = "unsupported weights / oob_mode / approximate_image2_gradient / use_depth_residual combination";
@@ -370,7 +378,8 @@ static int build_levels(dvo_handle* h, int frame_base, int n_frames, int with_gr
     }
     if (with_gradients != 2) {   // frames used as previous frames: their point lists
         for (int l = 0; l < h->levels; ++l) {
-            points_kernel<<<n_frames, 1024, 0, st>>>(h->gray[l] + (size_t)frame_base * h->lplane[l],
+            const size_t smem = points_smem_bytes((h->lw[l] + 127) / 128, h->lh[l]);
+            points_kernel<<<n_frames, 1024, smem, st>>>(h->gray[l] + (size_t)frame_base * h->lplane[l],
                                                      h->depth[l] + (size_t)frame_base * h->lplane[l],
                                                      h->prec[l] + 2 * (size_t)frame_base * h->lplane[l],
                                                      h->pt_tiles[l] + frame_base, h->depth_scale, h->lw[l], h->lh[l],
@@ -524,15 +533,16 @@ static void fill_params(const dvo_handle* h, AlignParams& p) {
         g.strips = h->lpitch[l] / kTile;
         g.n_tiles = g.strips * h->lh[l];
         g.h_magic = (unsigned)((1ull << 32) / (unsigned)h->lh[l]) + 1u;
-        {   // n_chunks = NW * k with about 60 tiles per chunk of a full point list (align_kernel.cuh, fused_pass).  The
-            // chunking fixes the summation order, so it depends on the image size and the launch shape only, never on
-            // the batch.  Measured (profiles/r2/kernel_experiments.jsonl): 120-tile chunks are 1 % faster on 4096 pairs,
-            // 60-tile chunks 2.4 % faster on 512 pairs (the tail kernel's clusters of 32 warps get 40 chunks, not 20).
+        {   // n_chunks = NW * k with about 75 tiles per chunk of a full point list (align_kernel.cuh, fused_pass): 32
+            // chunks at 640x480, one per warp of the tail kernel's clusters.  The chunking fixes the summation order,
+            // so it depends on the image size and the launch shape only, never on the batch.  Measured
+            // (profiles/r2/kernel_experiments.jsonl, tags chunk*): 60 / 75 / 90 tiles: 18.9 / 18.0 / 18.0 ms on 512
+            // pairs, 40.2 / 39.1 / 39.1 ms on 1184.
             const int nw = h->threads / 32;
             static const int target = [] {   // developer knob DVO_TUNE_CHUNK_ROWS (tiles per chunk aimed at)
                 const char* e = getenv("DVO_TUNE_CHUNK_ROWS");
                 const int v = e ? atoi(e) : 0;
-                return (v >= 8 && v <= 2048) ? v : 60;
+                return (v >= 8 && v <= 2048) ? v : 75;
             }();
             const int dense_tiles = (h->lw[l] * h->lh[l] + kTile - 1) / kTile;
             int k = (dense_tiles + nw * (target / 2)) / (nw * target);

@@ -106,70 +106,146 @@ __global__ void prec_fill_kernel(float* __restrict__ p, size_t n_floats) {
 
 // ---- a4 -----------------------------------------------------------------------------------------
 // The point list of one level of every frame (layout and order: align_kernel.cuh, "previous-frame point lists").
-// One CTA of 32 warps per frame walks the level strip by strip, 32 rows at a time: warp = row, lane = four columns
-// of the strip's 128; a block-wide exclusive scan of the per-thread counts gives every point its place in the list
-// (one __syncthreads per step: the warp totals alternate between two shared buffers).  The last tile is padded with
-// "no depth" points; pt_tiles[frame] receives the number of tiles.
+// One CTA of 32 warps per frame; a SEGMENT is one row of one 128-pixel strip (warp = segment, lane = four columns),
+// segments numbered strip-major.  Three phases, no barrier inside any loop:
+//   1  every warp counts the pixels with depth of its segments               -> s_cnt[segment]   (shared memory)
+//   2  block-wide exclusive scan of s_cnt: the place of every segment's first point in the list
+//   3  every warp re-reads its segments (L2 hits) and writes their points
+// The last tile is padded with "no depth" points; pt_tiles[frame] receives the number of tiles.
+// Dynamic shared memory: (strips * h + 64) ints + 32 KB of staging.
+inline size_t points_smem_bytes(int strips, int h) {
+    return ((size_t)strips * h + 64) * sizeof(int) + 32 * 256 * sizeof(float);
+}
+__device__ __forceinline__ int points_count4(uint2 dv) {
+    return ((dv.x & 0xffffu) != 0u) + ((dv.x >> 16) != 0u) + ((dv.y & 0xffffu) != 0u) + ((dv.y >> 16) != 0u);
+}
 __global__ void __launch_bounds__(1024) points_kernel(const uint8_t* __restrict__ gray, const uint16_t* __restrict__ depth,
                                                       float* __restrict__ list, int* __restrict__ pt_tiles,
                                                       double depth_scale, int w, int h, int pitch, size_t plane) {
-    __shared__ int s_tot[2][32];
+    extern __shared__ int s_cnt[];   // [n_seg] counts, then exclusive offsets; [n_seg .. n_seg + 31] warp totals of the scan
     const int frame = blockIdx.x;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint8_t* g8 = gray + (size_t)frame * plane;
     const uint16_t* d16 = depth + (size_t)frame * plane;
     float* out = list + 2u * (size_t)frame * plane;
     const int strips = (w + 127) >> 7;
-    int base = 0, buf = 0;
-    for (int s = 0; s < strips; ++s) {
-        const int col = s * 128 + 4 * lane;
-        for (int r0 = 0; r0 < h; r0 += 32) {
-            const int row = r0 + wid;
-            unsigned dd[4] = {0u, 0u, 0u, 0u};
-            unsigned gw = 0u;
-            if (row < h) {   // the padding columns of the depth plane are zero: no depth
-                const size_t e = (size_t)row * pitch + col;
-                const uint2 dv = __ldg(reinterpret_cast<const uint2*>(d16 + e));
-                gw = __ldg(reinterpret_cast<const unsigned*>(g8 + e));
-                dd[0] = dv.x & 0xffffu; dd[1] = dv.x >> 16; dd[2] = dv.y & 0xffffu; dd[3] = dv.y >> 16;
-            }
-            const int cnt = (dd[0] != 0u) + (dd[1] != 0u) + (dd[2] != 0u) + (dd[3] != 0u);
-            int incl = cnt;
+    const int n_seg = strips * h;
+    int* s_warp = s_cnt + n_seg;
+    // the padding columns of the depth plane are zero (no depth), so whole 128-column segments are read
+    auto seg_elem = [&](int seg) {
+        const int s = seg / h, row = seg - s * h;
+        return (size_t)row * pitch + (size_t)(s * 128 + 4 * lane);
+    };
+    // ---- 1: counts (four segments of the warp in flight)
+    for (int seg0 = wid; seg0 < n_seg; seg0 += 4 * 32) {
+        uint2 dv[4];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            if (lane == 31) s_tot[buf][wid] = incl;
-            __syncthreads();
-            int wincl = s_tot[buf][lane];   // inclusive scan of the 32 warp totals, in every warp
+        for (int k = 0; k < 4; ++k) {
+            const int seg = seg0 + 32 * k;
+            dv[k] = seg < n_seg ? __ldg(reinterpret_cast<const uint2*>(d16 + seg_elem(seg))) : make_uint2(0u, 0u);
+        }
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, wincl, o);
-                if (lane >= o) wincl += v;
-            }
-            const int before = __shfl_sync(0xffffffffu, wincl, (wid + 31) & 31);
-            const int total = __shfl_sync(0xffffffffu, wincl, 31);
-            int pos = base + (wid ? before : 0) + incl - cnt;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (dd[k] != 0u) {
-                    float* t = out + (size_t)(pos >> 7) * 256u + pt_index(pos & 127);
-                    t[0] = (float)((double)dd[k] * depth_scale);
-                    t[128] = __uint_as_float(pt_pack(col + k, row, (gw >> (8 * k)) & 255u));
-                    ++pos;
-                }
-            base += total;
-            buf ^= 1;
+        for (int k = 0; k < 4; ++k) {
+            const int seg = seg0 + 32 * k;
+            const int c = __reduce_add_sync(0xffffffffu, points_count4(dv[k]));
+            if (lane == 0 && seg < n_seg) s_cnt[seg] = c;
         }
     }
-    const int n_tiles = (base + 127) >> 7;
-    for (int pos = base + (int)threadIdx.x; pos < n_tiles * 128; pos += 1024) {
+    __syncthreads();
+    // ---- 2: exclusive scan of s_cnt (each thread a contiguous run, then warp and block level)
+    const int per = (n_seg + 1023) >> 10;
+    const int i0 = min(tid * per, n_seg), i1 = min(i0 + per, n_seg);
+    int run = 0;
+    for (int i = i0; i < i1; ++i) run += s_cnt[i];
+    int incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    int wincl = s_warp[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, wincl, o);
+        if (lane >= o) wincl += v;
+    }
+    const int before = __shfl_sync(0xffffffffu, wincl, (wid + 31) & 31);
+    const int total = __shfl_sync(0xffffffffu, wincl, 31);
+    int off = (wid ? before : 0) + incl - run;
+    for (int i = i0; i < i1; ++i) {
+        const int c = s_cnt[i];
+        s_cnt[i] = off;
+        off += c;
+    }
+    __syncthreads();
+    // ---- 3: the points.  A segment's points are consecutive in the list; the warp first lines them up in its
+    // staging buffer, then stores them tile word by tile word, 32 consecutive words per instruction.
+    float* stage_z = reinterpret_cast<float*>(s_warp + 32) + wid * 256;
+    unsigned* stage_w = reinterpret_cast<unsigned*>(stage_z) + 128;
+    for (int seg0 = wid; seg0 < n_seg; seg0 += 2 * 32) {
+        uint2 dv[2];
+        unsigned gw[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int seg = seg0 + 32 * k;
+            dv[k] = make_uint2(0u, 0u);
+            gw[k] = 0u;
+            if (seg < n_seg) {
+                const size_t e = seg_elem(seg);
+                dv[k] = __ldg(reinterpret_cast<const uint2*>(d16 + e));
+                gw[k] = __ldg(reinterpret_cast<const unsigned*>(g8 + e));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int seg = seg0 + 32 * k;
+            if (seg >= n_seg) break;
+            const int s = seg / h, row = seg - s * h;
+            const int col = s * 128 + 4 * lane;
+            const unsigned dd[4] = {dv[k].x & 0xffffu, dv[k].x >> 16, dv[k].y & 0xffffu, dv[k].y >> 16};
+            const int cnt = points_count4(dv[k]);
+            int lincl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, lincl, o);
+                if (lane >= o) lincl += v;
+            }
+            const int n_pts = __shfl_sync(0xffffffffu, lincl, 31);
+            int q = lincl - cnt;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (dd[j] != 0u) {
+                    stage_z[q] = (float)((double)dd[j] * depth_scale);
+                    stage_w[q] = pt_pack(col + j, row, (gw[k] >> (8 * j)) & 255u);
+                    ++q;
+                }
+            __syncwarp();
+            const int first = s_cnt[seg], last = first + n_pts;   // list positions [first, last)
+            for (int tile = first >> 7; tile * 128 < last; ++tile) {
+                float* t = out + (size_t)tile * 256u;
+#pragma unroll
+                for (int i0w = 0; i0w < 128; i0w += 32) {
+                    const int i = i0w + lane;                                            // word of the tile's z half
+                    const int j = ((i >> 6) << 6) | ((i & 1) << 5) | ((i >> 1) & 31);    // inverse of pt_index
+                    const int pos = tile * 128 + j;
+                    if (pos >= first && pos < last) {
+                        t[i] = stage_z[pos - first];
+                        t[i + 128] = __uint_as_float(stage_w[pos - first]);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    const int n_tiles = (total + 127) >> 7;
+    for (int pos = total + tid; pos < n_tiles * 128; pos += 1024) {
         float* t = out + (size_t)(pos >> 7) * 256u + pt_index(pos & 127);
         t[0] = __uint_as_float(kPrecNoDepth);
         t[128] = 0.0f;
     }
-    if (threadIdx.x == 0) pt_tiles[frame] = n_tiles;
+    if (tid == 0) pt_tiles[frame] = n_tiles;
 }
 
 // ---- a2 -----------------------------------------------------------------------------------------

@@ -107,7 +107,7 @@ void dvo_default_config(dvo_config* cfg);
 
 /* Replaces the estimator constructor (RobustDVOGPU.__init__, gpu_robust_dense_visual_odometry.py:16-47:
  * fixed resolution, everything preallocated).  Allocates pyramids for max_frames frame slots and
- * state for max_pairs pairs per estimate call. */
+ * state for max_pairs pairs per estimate call.  height and width at most 2048 (DVO_ERR_INVALID beyond). */
 int dvo_create(dvo_handle** out, int device, int height, int width, int levels, int max_frames, int max_pairs,
                const dvo_config* cfg);
 int dvo_destroy(dvo_handle* h);
@@ -121,9 +121,9 @@ int dvo_set_intrinsics(dvo_handle* h, float fx, float fy, float cx, float cy, do
  * far depth -> 0 IN PLACE) followed by _build_pyramids (cpu_...py:44-52 -> image_pyramid.py:19-54) and
  * _setup's Sobel planes (cpu_...py:58 -> jacobian.py:70-71) for n_frames frames stored in slots
  * frame_base..frame_base+n_frames-1.  bgr: [n,H,W,3] u8, depth: [n,H,W] u16.  with_gradients names the role(s)
- * the frames will play: 0 = previous frames only (no gradient planes), 1 = both roles (a sequence: every frame is
- * first "current", then "previous"), 2 = current frames only (gradient planes, no metric-depth planes).
- * dvo_set_intrinsics must have been called: the depth scale enters the previous-frame planes
+ * the frames will play: 0 = previous frames only (point lists, no gradient planes), 1 = both roles (a sequence: every frame is
+ * first "current", then "previous"), 2 = current frames only (gradient planes, no point lists).
+ * dvo_set_intrinsics must have been called: the depth scale enters the previous-frame point lists
  * (camera_model.py:199-200, z = depth * depth_scale, is evaluated here, once per frame, not per iteration). */
 /* At most 65535 frames per call. */
 int dvo_build_pyramids(dvo_handle* h, int frame_base, const uint8_t* bgr_dev, uint16_t* depth_dev, int n_frames,
