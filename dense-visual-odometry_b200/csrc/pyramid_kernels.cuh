@@ -249,47 +249,60 @@ __global__ void __launch_bounds__(1024) points_kernel(const uint8_t* __restrict_
 }
 
 // ---- a2 -----------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ void cswap(T& a, T& b) {
-    const T lo = a < b ? a : b;
-    const T hi = a < b ? b : a;
+// Medians run two at a time in the 16-bit halves of a register (VIMNMX.U16x2: one instruction is a packed
+// min or max).  u16 depths are the halves themselves; a u8 intensity v travels as the key v * 257 (its byte
+// duplicated by the same byte permute that extracts it), which orders like v and carries v in its low byte.
+__device__ __forceinline__ void cswap2(unsigned& a, unsigned& b) {
+    const unsigned lo = __vminu2(a, b);
+    const unsigned hi = __vmaxu2(a, b);
     a = lo;
     b = hi;
 }
 
-// Median of nine with the classic 19 compare-exchange network.
-template <typename T>
-__device__ __forceinline__ T median9(T p0, T p1, T p2, T p3, T p4, T p5, T p6, T p7, T p8) {
-    cswap(p1, p2); cswap(p4, p5); cswap(p7, p8);
-    cswap(p0, p1); cswap(p3, p4); cswap(p6, p7);
-    cswap(p1, p2); cswap(p4, p5); cswap(p7, p8);
-    cswap(p0, p3); cswap(p5, p8); cswap(p4, p7);
-    cswap(p3, p6); cswap(p1, p4); cswap(p2, p5);
-    cswap(p4, p7); cswap(p4, p2); cswap(p6, p4);
-    cswap(p4, p2);
+// Median of nine with the classic 19 compare-exchange network, on two independent sets at once.
+__device__ __forceinline__ unsigned median9x2(unsigned p0, unsigned p1, unsigned p2, unsigned p3, unsigned p4, unsigned p5,
+                                              unsigned p6, unsigned p7, unsigned p8) {
+    cswap2(p1, p2); cswap2(p4, p5); cswap2(p7, p8);
+    cswap2(p0, p1); cswap2(p3, p4); cswap2(p6, p7);
+    cswap2(p1, p2); cswap2(p4, p5); cswap2(p7, p8);
+    cswap2(p0, p3); cswap2(p5, p8); cswap2(p4, p7);
+    cswap2(p3, p6); cswap2(p1, p4); cswap2(p2, p5);
+    cswap2(p4, p7); cswap2(p4, p2); cswap2(p6, p4);
+    cswap2(p4, p2);
     return p4;
 }
 
-// Nine source values of one row feeding FOUR consecutive outputs ox = 4k .. 4k+3: source columns
-// 8k-1 .. 8k+7, border replicated.  Interior threads use one scalar + one 8-element vector load (rows start
-// 16-byte aligned because every pitch is a multiple of 64); the first and the last thread of a row clamp.
+// FOUR consecutive outputs ox = 4k .. 4k+3 of a row need source columns v_0 .. v_8 = 8k-1 .. 8k+7 (border replicated):
+// output j uses v_2j, v_2j+1, v_2j+2.  Outputs (0, 2) and (1, 3) are paired, so one source row contributes the five
+// packed words A_c = (v_c, v_c+4), c = 0..4: outputs (0, 2) take A_0 A_1 A_2, outputs (1, 3) take A_2 A_3 A_4.
+// Interior threads use one scalar + one 8-element vector load (rows start 16-byte aligned because every pitch is a
+// multiple of 64) and five byte permutes; the first and the last thread of a row clamp.
 template <typename T>
-__device__ __forceinline__ void load_row9(const T* __restrict__ row, int k, int sw, int* v) {
+__device__ __forceinline__ void load_row5x2(const T* __restrict__ row, int k, int sw, unsigned* A) {
     const int c0 = 8 * k;
     if (k > 0 && c0 + 7 < sw) {
-        v[0] = (int)__ldg(row + c0 - 1);
+        const unsigned v0 = (unsigned)__ldg(row + c0 - 1);
         if (sizeof(T) == 1) {
-            const uint2 w = __ldg(reinterpret_cast<const uint2*>(row + c0));
-            v[1] = w.x & 255u; v[2] = (w.x >> 8) & 255u; v[3] = (w.x >> 16) & 255u; v[4] = w.x >> 24;
-            v[5] = w.y & 255u; v[6] = (w.y >> 8) & 255u; v[7] = (w.y >> 16) & 255u; v[8] = w.y >> 24;
+            const uint2 w = __ldg(reinterpret_cast<const uint2*>(row + c0));   // bytes v1..v4, v5..v8
+            A[0] = __byte_perm(v0, w.x, 0x7700);
+            A[1] = __byte_perm(w.x, w.y, 0x4400);
+            A[2] = __byte_perm(w.x, w.y, 0x5511);
+            A[3] = __byte_perm(w.x, w.y, 0x6622);
+            A[4] = __byte_perm(w.x, w.y, 0x7733);
         } else {
-            const uint4 w = __ldg(reinterpret_cast<const uint4*>(row + c0));
-            v[1] = w.x & 65535u; v[2] = w.x >> 16; v[3] = w.y & 65535u; v[4] = w.y >> 16;
-            v[5] = w.z & 65535u; v[6] = w.z >> 16; v[7] = w.w & 65535u; v[8] = w.w >> 16;
+            const uint4 w = __ldg(reinterpret_cast<const uint4*>(row + c0));   // halves (v1,v2) (v3,v4) (v5,v6) (v7,v8)
+            A[0] = __byte_perm(v0, w.y, 0x7610);
+            A[1] = __byte_perm(w.x, w.z, 0x5410);
+            A[2] = __byte_perm(w.x, w.z, 0x7632);
+            A[3] = __byte_perm(w.y, w.w, 0x5410);
+            A[4] = __byte_perm(w.y, w.w, 0x7632);
         }
     } else {
+        unsigned v[9];
 #pragma unroll
-        for (int j = 0; j < 9; ++j) v[j] = (int)__ldg(row + min(max(c0 - 1 + j, 0), sw - 1));
+        for (int j = 0; j < 9; ++j) v[j] = (unsigned)__ldg(row + min(max(c0 - 1 + j, 0), sw - 1));
+#pragma unroll
+        for (int c = 0; c < 5; ++c) A[c] = v[c] | (v[c + 4] << 16);
     }
 }
 
@@ -313,28 +326,25 @@ __global__ void __launch_bounds__(128) median3_down_pair_kernel(const uint8_t* _
     const size_t ra = (size_t)max(cy - 1, 0) * spitch, rb = (size_t)cy * spitch, rc = (size_t)min(cy + 1, sh - 1) * spitch;
     const uint8_t* s8 = src8 + (size_t)frame * splane;
     const uint16_t* s16 = src16 + (size_t)frame * splane;
-    int a0[9], a1[9], a2[9], b0[9], b1[9], b2[9];
-    load_row9(s8 + ra, k, sw, a0);
-    load_row9(s8 + rb, k, sw, a1);
-    load_row9(s8 + rc, k, sw, a2);
-    load_row9(s16 + ra, k, sw, b0);
-    load_row9(s16 + rb, k, sw, b1);
-    load_row9(s16 + rc, k, sw, b2);
-    int m[4], n[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        m[j] = median9<int>(a0[2 * j], a0[2 * j + 1], a0[2 * j + 2], a1[2 * j], a1[2 * j + 1], a1[2 * j + 2],
-                            a2[2 * j], a2[2 * j + 1], a2[2 * j + 2]);
-        n[j] = median9<int>(b0[2 * j], b0[2 * j + 1], b0[2 * j + 2], b1[2 * j], b1[2 * j + 1], b1[2 * j + 2],
-                            b2[2 * j], b2[2 * j + 1], b2[2 * j + 2]);
-    }
+    unsigned a0[5], a1[5], a2[5], b0[5], b1[5], b2[5];
+    load_row5x2(s8 + ra, k, sw, a0);
+    load_row5x2(s8 + rb, k, sw, a1);
+    load_row5x2(s8 + rc, k, sw, a2);
+    load_row5x2(s16 + ra, k, sw, b0);
+    load_row5x2(s16 + rb, k, sw, b1);
+    load_row5x2(s16 + rc, k, sw, b2);
+    // medians of outputs (0, 2) and (1, 3)
+    const unsigned m02 = median9x2(a0[0], a0[1], a0[2], a1[0], a1[1], a1[2], a2[0], a2[1], a2[2]);
+    const unsigned m13 = median9x2(a0[2], a0[3], a0[4], a1[2], a1[3], a1[4], a2[2], a2[3], a2[4]);
+    const unsigned n02 = median9x2(b0[0], b0[1], b0[2], b1[0], b1[1], b1[2], b2[0], b2[1], b2[2]);
+    const unsigned n13 = median9x2(b0[2], b0[3], b0[4], b1[2], b1[3], b1[4], b2[2], b2[3], b2[4]);
     const size_t o = (size_t)frame * dplane + (size_t)oy * dpitch + ox;
     if (ox + 3 < dw) {
-        *reinterpret_cast<uint32_t*>(dst8 + o) =
-            (uint32_t)m[0] | ((uint32_t)m[1] << 8) | ((uint32_t)m[2] << 16) | ((uint32_t)m[3] << 24);
-        *reinterpret_cast<uint2*>(dst16 + o) =
-            make_uint2((uint32_t)n[0] | ((uint32_t)n[1] << 16), (uint32_t)n[2] | ((uint32_t)n[3] << 16));
+        *reinterpret_cast<uint32_t*>(dst8 + o) = __byte_perm(m02, m13, 0x6240);   // the low bytes of the four keys
+        *reinterpret_cast<uint2*>(dst16 + o) = make_uint2(__byte_perm(n02, n13, 0x5410), __byte_perm(n02, n13, 0x7632));
     } else {
+        const unsigned m[4] = {m02 & 255u, m13 & 255u, (m02 >> 16) & 255u, (m13 >> 16) & 255u};
+        const unsigned n[4] = {n02 & 0xffffu, n13 & 0xffffu, n02 >> 16, n13 >> 16};
         for (int j = 0; j < 4 && ox + j < dw; ++j) {   // padding columns keep their initial state
             dst8[o + j] = (uint8_t)m[j];
             dst16[o + j] = (uint16_t)n[j];
