@@ -478,7 +478,7 @@ def other_configs(torch, dvo, dev, args):
     out["c2_tdist_sequence_1000"] = config_sequence(torch, dvo, dev, 1000, "tdist")
     out["c2_tdist_batch"] = config_batch(torch, dvo, dev, H, W, LEVELS, 1184, 3, weights="tdist", e2e=False)
     out["c4_1280x720_depth"] = config_batch(torch, dvo, dev, 720, 1280, 5, 592, 2, depth=True)
-    out["c4_1920x1080_depth"] = config_batch(torch, dvo, dev, 1080, 1920, 5, 296, 2, depth=True)
+    out["c4_1920x1080_depth"] = config_batch(torch, dvo, dev, 1080, 1920, 5, 592, 2, depth=True)
     out["seconds"] = time.perf_counter() - t0
     return out
 
