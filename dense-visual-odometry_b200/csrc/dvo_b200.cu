@@ -9,6 +9,7 @@
 
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/dvo_b200.h"
 #include "align_kernel.cuh"
@@ -33,6 +34,7 @@ struct dvo_handle {
     uint2* rec[DVO_MAX_LEVELS]{};
     float* prec[DVO_MAX_LEVELS]{};   // previous-frame point lists, room for 2 words per pixel (align_kernel.cuh, pt_pack)
     int* pt_tiles[DVO_MAX_LEVELS]{};   // [frame] tiles of the frame's point list
+    std::vector<uint8_t> slot_built;   // per frame slot: kHasPoints | kHasTaps, what the last build of the slot produced
     float k4[DVO_MAX_LEVELS][4]{}, kinv4[DVO_MAX_LEVELS][4]{};
     int* queue = nullptr;   // kQueueSlots x 4 work-queue counters; concurrent dvo_estimate calls (different streams) rotate through them
     int queue_next = 0;
@@ -177,6 +179,22 @@ extern "C" int dvo_destroy(dvo_handle* h) {
     return DVO_OK;
 }
 
+constexpr uint8_t kHasPoints = 1, kHasTaps = 2;
+
+// The roles the frames of an estimate must have been built for (dvo_build_pyramids, with_gradients).
+static int check_roles(dvo_handle* h, int prev_base, int cur_base, int n, bool prev_needs_taps) {
+    const uint8_t prev_need = kHasPoints | (prev_needs_taps ? kHasTaps : 0);
+    for (int i = 0; i < n; ++i) {
+        if ((h->slot_built[prev_base + i] & prev_need) != prev_need)
+            return fail(h, DVO_ERR_STATE, prev_needs_taps
+                ? "a previous-frame slot was not built with with_gradients = 1 (approximate_image2_gradient needs both roles)"
+                : "a previous-frame slot was not built as a previous frame (with_gradients 0 or 1)");
+        if (!(h->slot_built[cur_base + i] & kHasTaps))
+            return fail(h, DVO_ERR_STATE, "a current-frame slot was not built as a current frame (with_gradients 1 or 2)");
+    }
+    return DVO_OK;
+}
+
 static int create_impl(dvo_handle* h) {
     DVO_CUDA(h, cudaSetDevice(h->device));
     cudaDeviceProp prop;
@@ -300,6 +318,7 @@ extern "C" int dvo_create(dvo_handle** out, int device, int height, int width, i
     h->W = width;
     h->levels = levels;
     h->max_frames = max_frames;
+    h->slot_built.assign((size_t)max_frames, 0);
     h->max_pairs = max_pairs;
     if (cfg)
         h->cfg = *cfg;
@@ -425,6 +444,8 @@ static int build_impl(dvo_handle* h, int frame_base, const uint8_t* img, uint16_
     else DVO_LAUNCH_GC(false, false);
 #undef DVO_LAUNCH_GC
     h->launches += 1;
+    for (int i = 0; i < n_frames; ++i)
+        h->slot_built[frame_base + i] = (uint8_t)((with_gradients != 2 ? kHasPoints : 0) | (with_gradients != 0 ? kHasTaps : 0));
     return build_levels(h, frame_base, n_frames, with_gradients, st);
 }
 
@@ -504,6 +525,8 @@ extern "C" int dvo_get_point_list(dvo_handle* h, int slot, int level, float* z_d
     if (!h) return DVO_ERR_INVALID;
     if (slot < 0 || slot >= h->max_frames || level < 0 || level >= h->levels)
         return fail(h, DVO_ERR_RANGE, "slot / level out of range");
+    if (!(h->slot_built[slot] & kHasPoints))
+        return fail(h, DVO_ERR_STATE, "the slot was not built as a previous frame (with_gradients 0 or 1)");
     DVO_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int cap = h->lw[level] * h->lh[level];
@@ -624,6 +647,10 @@ extern "C" int dvo_estimate(dvo_handle* h, int prev_base, int cur_base, int n_pa
         cur_base + n_pairs > h->max_frames)
         return fail(h, DVO_ERR_RANGE, "pair range exceeds the frame slots");
     if (n_pairs > h->max_pairs) return fail(h, DVO_ERR_RANGE, "n_pairs exceeds max_pairs");
+    {
+        const int rc = check_roles(h, prev_base, cur_base, n_pairs, h->cfg.approximate_image2_gradient != 0);
+        if (rc != DVO_OK) return rc;
+    }
     DVO_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     AlignParams p;
@@ -746,6 +773,9 @@ extern "C" int dvo_residuals_jacobian(dvo_handle* h, int prev_slot, int cur_slot
     if (prev_slot < 0 || prev_slot >= h->max_frames || cur_slot < 0 || cur_slot >= h->max_frames || level < 0 ||
         level >= h->levels)
         return fail(h, DVO_ERR_RANGE, "slot / level out of range");
+    if (!h->slot_built[prev_slot] || !(h->slot_built[cur_slot] & kHasTaps) ||
+        (h->cfg.approximate_image2_gradient && !(h->slot_built[prev_slot] & kHasTaps)))
+        return fail(h, DVO_ERR_STATE, "the slots were not built for these roles (dvo_build_pyramids, with_gradients)");
     DVO_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     AlignParams p;
@@ -773,6 +803,9 @@ extern "C" int dvo_depth_residuals_jacobian(dvo_handle* h, int prev_slot, int cu
     if (prev_slot < 0 || prev_slot >= h->max_frames || cur_slot < 0 || cur_slot >= h->max_frames || level < 0 ||
         level >= h->levels)
         return fail(h, DVO_ERR_RANGE, "slot / level out of range");
+    if (!h->slot_built[prev_slot] || !(h->slot_built[cur_slot] & kHasTaps) ||
+        (h->cfg.approximate_image2_gradient && !(h->slot_built[prev_slot] & kHasTaps)))
+        return fail(h, DVO_ERR_STATE, "the slots were not built for these roles (dvo_build_pyramids, with_gradients)");
     DVO_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     AlignParams p;

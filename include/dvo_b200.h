@@ -124,7 +124,9 @@ int dvo_set_intrinsics(dvo_handle* h, float fx, float fy, float cx, float cy, do
  * the frames will play: 0 = previous frames only (point lists, no gradient planes), 1 = both roles (a sequence: every frame is
  * first "current", then "previous"), 2 = current frames only (gradient planes, no point lists).
  * dvo_set_intrinsics must have been called: the depth scale enters the previous-frame point lists
- * (camera_model.py:199-200, z = depth * depth_scale, is evaluated here, once per frame, not per iteration). */
+ * (camera_model.py:199-200, z = depth * depth_scale, is evaluated here, once per frame, not per iteration).
+ * The handle remembers what every slot was built for: dvo_estimate and the dense hooks return DVO_ERR_STATE when a slot
+ * is used in a role it was not built for. */
 /* At most 65535 frames per call. */
 int dvo_build_pyramids(dvo_handle* h, int frame_base, const uint8_t* bgr_dev, uint16_t* depth_dev, int n_frames,
                        int with_gradients, void* stream);

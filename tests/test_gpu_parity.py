@@ -3,6 +3,7 @@ host mirror, is compared with (a) the CPU oracle on the same inputs and (b) gold
 REAL reference (tests/golden/).  Tolerances follow BASELINE.json's north_star:
   pyramid indexing and validity masks: bit-exact; residuals / Jacobians: 1e-5 relative (to the plane's
   max magnitude); final pose: 1e-4 rad / 1e-4 m."""
+import ctypes as C
 import hashlib
 import json
 import os
@@ -427,6 +428,22 @@ def test_errors_are_loud(dvo_mod):
     est.step(np.zeros((8, 8, 3), np.uint8), np.ones((8, 8), np.uint16))
     with pytest.raises(ValueError):
         est.step(np.zeros((9, 8, 3), np.uint8), np.ones((9, 8), np.uint16))
+    # a frame slot used in a role it was not built for (no point list / no tap records) is refused, not read
+    import torch
+    dev = torch.device("cuda", 0)
+    al = m.PairBatchAligner(cam, 16, 16, 1, max_pairs=2)
+    bgr = torch.zeros((2, 16, 16, 3), dtype=torch.uint8, device=dev)
+    dep = torch.ones((2, 16, 16), dtype=torch.uint16, device=dev)
+    with pytest.raises(m.DvoError, match="not built"):
+        al._B = 2
+        al.estimate()                                   # nothing built yet
+    al.build(bgr, dep, bgr, dep)
+    al.estimate()
+    h = al.handle
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    h.call("dvo_build_pyramids", 0, C.c_void_p(bgr.data_ptr()), C.c_void_p(dep.data_ptr()), 2, 2, st)   # current-only
+    with pytest.raises(m.DvoError, match="previous frame"):
+        al.estimate()
 
 
 # ------------------------------------------------------------------------------------------------ sequences
