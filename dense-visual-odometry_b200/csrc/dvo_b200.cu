@@ -408,7 +408,7 @@ static int build_levels(dvo_handle* h, int frame_base, int n_frames, int with_gr
     }
     if (with_gradients) {
         for (int l = 0; l < h->levels; ++l) {
-            dim3 grid(((h->lw[l] + 3) / 4 * h->lh[l] + 127) / 128, n_frames);
+            dim3 grid(((h->lw[l] + 7) / 8 * h->lh[l] + 127) / 128, n_frames);
             sobel3_kernel<<<grid, 128, 0, st>>>(h->gray[l] + (size_t)frame_base * h->lplane[l],
                                                 h->depth[l] + (size_t)frame_base * h->lplane[l],
                                                 h->rec[l] + (size_t)frame_base * h->lplane[l], h->lw[l], h->lh[l],

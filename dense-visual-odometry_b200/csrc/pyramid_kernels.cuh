@@ -353,51 +353,54 @@ __global__ void __launch_bounds__(128) median3_down_pair_kernel(const uint8_t* _
 }
 
 // ---- a9 -----------------------------------------------------------------------------------------
-// One thread per FOUR pixels of a row: columns 4k-1 .. 4k+4 of three rows (one 32-bit load + two bytes each),
-// four packed records out as two 16-byte stores.
-__device__ __forceinline__ void load_row6(const uint8_t* __restrict__ row, int x0, int w, int* v) {
+// One thread per EIGHT pixels of a row: columns 8k-1 .. 8k+8 of three rows (one 64-bit load + two bytes each),
+// eight packed records out as four 16-byte stores.
+__device__ __forceinline__ void load_row10(const uint8_t* __restrict__ row, int x0, int w, int* v) {
     v[0] = (int)__ldg(row + max(x0 - 1, 0));
-    if (x0 + 3 < w) {
-        const uint32_t q = __ldg(reinterpret_cast<const uint32_t*>(row + x0));
-        v[1] = q & 255u; v[2] = (q >> 8) & 255u; v[3] = (q >> 16) & 255u; v[4] = q >> 24;
+    if (x0 + 7 < w) {
+        const uint2 q = __ldg(reinterpret_cast<const uint2*>(row + x0));
+        v[1] = q.x & 255u; v[2] = (q.x >> 8) & 255u; v[3] = (q.x >> 16) & 255u; v[4] = q.x >> 24;
+        v[5] = q.y & 255u; v[6] = (q.y >> 8) & 255u; v[7] = (q.y >> 16) & 255u; v[8] = q.y >> 24;
     } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[1 + j] = (int)__ldg(row + min(x0 + j, w - 1));
+        for (int j = 0; j < 8; ++j) v[1 + j] = (int)__ldg(row + min(x0 + j, w - 1));
     }
-    v[5] = (int)__ldg(row + min(x0 + 4, w - 1));
+    v[9] = (int)__ldg(row + min(x0 + 8, w - 1));
 }
 
 __global__ void __launch_bounds__(128) sobel3_kernel(const uint8_t* __restrict__ gray, const uint16_t* __restrict__ depth,
                                                      uint2* __restrict__ rec, int w, int h, int pitch, size_t plane) {
-    // threads numbered linearly over (row, 4-pixel group): narrow levels still fill their blocks
-    const int gpr = (w + 3) >> 2;
+    // threads numbered linearly over (row, 8-pixel group): narrow levels still fill their blocks
+    const int gpr = (w + 7) >> 3;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= gpr * h) return;
     const int y = idx / gpr;
-    const int x0 = 4 * (idx - y * gpr);
+    const int x0 = 8 * (idx - y * gpr);
     const int frame = blockIdx.y;
     const uint8_t* s = gray + (size_t)frame * plane;
-    int a[6], b[6], c[6];
-    load_row6(s + (size_t)max(y - 1, 0) * pitch, x0, w, a);
-    load_row6(s + (size_t)y * pitch, x0, w, b);
-    load_row6(s + (size_t)min(y + 1, h - 1) * pitch, x0, w, c);
-    // the pixel's depth rides in the record too (padding columns of the depth plane are zero, and so are the four
-    // values of a partial group beyond the image: the 8-byte load stays inside the row's pitch)
-    const uint2 dw = __ldg(reinterpret_cast<const uint2*>(depth + (size_t)frame * plane + (size_t)y * pitch + x0));
-    const unsigned dd[4] = {dw.x & 0xffffu, dw.x >> 16, dw.y & 0xffffu, dw.y >> 16};
-    uint2 out[4];
+    int a[10], b[10], c[10];
+    load_row10(s + (size_t)max(y - 1, 0) * pitch, x0, w, a);
+    load_row10(s + (size_t)y * pitch, x0, w, b);
+    load_row10(s + (size_t)min(y + 1, h - 1) * pitch, x0, w, c);
+    // the pixel's depth rides in the record too (padding columns of the depth plane are zero, and so are the
+    // values of a partial group beyond the image: the 16-byte load stays inside the row's pitch)
+    const uint4 dw = __ldg(reinterpret_cast<const uint4*>(depth + (size_t)frame * plane + (size_t)y * pitch + x0));
+    const unsigned dd[8] = {dw.x & 0xffffu, dw.x >> 16, dw.y & 0xffffu, dw.y >> 16,
+                            dw.z & 0xffffu, dw.z >> 16, dw.w & 0xffffu, dw.w >> 16};
+    uint2 out[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 8; ++j) {
         const int gx = (a[j + 2] + 2 * b[j + 2] + c[j + 2]) - (a[j] + 2 * b[j] + c[j]);
         const int gy = (c[j] + 2 * c[j + 1] + c[j + 2]) - (a[j] + 2 * a[j + 1] + a[j + 2]);
         out[j] = rec_pack(gx, gy, b[j + 1], dd[j]);
     }
     uint2* d = rec + (size_t)frame * plane + (size_t)y * pitch + x0;
-    if (x0 + 3 < w) {
-        reinterpret_cast<uint4*>(d)[0] = make_uint4(out[0].x, out[0].y, out[1].x, out[1].y);
-        reinterpret_cast<uint4*>(d)[1] = make_uint4(out[2].x, out[2].y, out[3].x, out[3].y);
+    if (x0 + 7 < w) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            reinterpret_cast<uint4*>(d)[j] = make_uint4(out[2 * j].x, out[2 * j].y, out[2 * j + 1].x, out[2 * j + 1].y);
     } else {
-        for (int j = 0; j < 4 && x0 + j < w; ++j) d[j] = out[j];   // padding columns stay zero
+        for (int j = 0; j < 8 && x0 + j < w; ++j) d[j] = out[j];   // padding columns stay zero
     }
 }
 
