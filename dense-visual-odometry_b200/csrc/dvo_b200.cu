@@ -598,6 +598,14 @@ static void fill_params(const dvo_handle* h, AlignParams& p) {
     p.tdist_tol = h->cfg.tdist_tolerance;
     p.tdist_max_iter = h->cfg.tdist_max_iterations;
     p.tdist_mean = h->cfg.tdist_mean ? 1 : 0;
+    {   // developer knob DVO_TUNE_SPEC_TOL: acceptance bound of the speculated t-distribution weights
+        static const float tol = [] {
+            const char* e = getenv("DVO_TUNE_SPEC_TOL");
+            const double v = e ? atof(e) : 0.0;
+            return (v > 0.0 && v <= 1e-2) ? (float)v : (float)kTdSpecTol;
+        }();
+        p.tdist_spec_tol = tol;
+    }
     p.huber_k = h->cfg.huber_k;
     const float s_hi = (float)h->depth_scale;
     p.scale_hi = s_hi;
