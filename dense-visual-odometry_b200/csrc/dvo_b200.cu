@@ -272,7 +272,14 @@ static int create_impl(dvo_handle* h) {
             h->err = "image too large for the point-list build (strips x rows of level 0 must fit shared memory)";
             return DVO_ERR_INVALID;
         }
-        DVO_CUDA(h, cudaFuncSetAttribute((const void*)points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // the attribute belongs to the function on this device, not to the handle: handles of different image sizes
+        // share it, so it is only ever raised
+        static size_t granted[64] = {};
+        const int di = h->device & 63;
+        if (smem > granted[di]) {
+            DVO_CUDA(h, cudaFuncSetAttribute((const void*)points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            granted[di] = smem;
+        }
     }
     align_fn fn = get_align(h);
     if (!fn) {

@@ -120,6 +120,22 @@ def test_point_list_bit_exact(dvo_mod, testdata_frames):
                 assert np.array_equal(a, b)
 
 
+def test_point_lists_of_handles_of_different_sizes(dvo_mod):
+    """The point-list kernel's shared-memory opt-in belongs to the function, not the handle: a small handle created
+    after a large one must not take it away from the large one."""
+    rng = np.random.default_rng(3)
+    big = _estimator(dvo_mod, (1000.0, 1000.0, 960.0, 540.0), 1e-9, 2)
+    g8 = rng.integers(0, 256, (1080, 1920), dtype=np.uint8)
+    d16 = rng.integers(0, 65536, (1080, 1920), dtype=np.uint16)
+    big.step(np.repeat(g8[..., None], 3, -1), d16.copy())
+    small = _estimator(dvo_mod, (100.0, 100.0, 32.0, 24.0), 1e-9, 2)
+    small.step(np.zeros((48, 64, 3), np.uint8), np.ones((48, 64), np.uint16))
+    big.step(np.repeat(g8[..., None], 3, -1), d16.copy())          # launches the 1080p point-list build again
+    z, col, row, inten = big.get_point_list(big._prev_slot, 0)
+    want = _expected_point_list(g8, d16, 1e-9)
+    assert np.array_equal(col, want[1]) and np.array_equal(row, want[2]) and np.array_equal(inten, want[3])
+
+
 def test_gray_conversion_lattice(dvo_mod, golden_dir):
     prim = json.loads((golden_dir / "primitives.json").read_text())
     rng = np.random.default_rng(7)
