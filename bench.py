@@ -389,7 +389,7 @@ def config_batch(torch, dvo, dev, height, width, levels, pairs, steps, weights="
         for hbuf, x in zip(hb, tensors):
             hbuf.copy_(x)
         torch.cuda.synchronize(dev)
-        sec, h2d, d2h, qt_e = time_e2e(torch, al, hb, pairs, max(2, steps // 2), 1, dev, 1, 256 if width <= 640 else 32)
+        sec, h2d, d2h, qt_e = time_e2e(torch, al, hb, pairs, max(2, steps // 2), 1, dev, 1, 256 if width <= 640 else 148)
         rec["e2e"] = {"value": pairs * max(2, steps // 2) / sec, "unit": UNIT, "h2d_bytes_per_step": h2d,
                       "d2h_bytes_per_step": d2h, "matches_resident": bool(np.array_equal(qt_e, qt_h))}
         del hb

@@ -692,6 +692,19 @@ extern "C" int dvo_estimate(dvo_handle* h, int prev_base, int cur_base, int n_pa
             return v < 0 ? 0 : v;
         }();
         p.quantum_tiles = (n_pairs > grid) ? q0 * p.lv[0].n_tiles : 0;
+        // Launches in which every pair has a CTA of its own (n_pairs <= grid) run in time slices too: once a tenth of
+        // the pairs are finished, the CTAs that find the queue empty raise the draining flag, the others park their pair
+        // at the end of its slice and the tail kernel's clusters finish the rest on all SMs (instead of the launch ending
+        // on its longest pair with most SMs idle).  Measured (profiles/r2/kernel_experiments.jsonl, tags rtc / slice_*):
+        // 8 pairs 6.6 -> 4.1 ms, 32 pairs 8.7 -> 6.0, 256 pairs 15.1 -> 10.9, 296 pairs at 1920x1080 122 -> 68.
+        // Developer knobs: DVO_TUNE_SLICE_MIN = smallest such launch (pairs; 0 = never), DVO_TUNE_DRAIN_PCT.
+        static const int slice_min = [] { const char* e = getenv("DVO_TUNE_SLICE_MIN"); return e ? atoi(e) : 2; }();
+        static const int drain_pct = [] { const char* e = getenv("DVO_TUNE_DRAIN_PCT"); return e ? atoi(e) : 10; }();
+        p.drain_after = 0;
+        if (n_pairs <= grid && slice_min > 0 && n_pairs >= slice_min) {
+            p.quantum_tiles = q0 * p.lv[0].n_tiles;
+            p.drain_after = (int)((long long)n_pairs * drain_pct / 100);
+        }
     }
     // tail kernel: clusters of `tail_c` CTAs finish the pairs still running when the persistent kernel's queue runs
     // dry (developer knob DVO_TUNE_TAIL_CLUSTER: 0 = off, 2, 4 or 8)

@@ -602,27 +602,42 @@ class SequenceAligner:
         for s in self._streams:
             s.wait_stream(cur)
         cp = C.c_void_p(cs.cuda_stream)
-        built = None  # event: the previous chunk's pyramids are complete
-        for k, lo in enumerate(range(0, N, chunk_frames)):
-            hi = min(lo + chunk_frames, N)
-            s = self._streams[k % 3]
+        # Frames arrive in chunks of chunk_frames (upload on the copy stream, pyramids as soon as a chunk has landed).
+        # Estimates are launched per GROUP of chunks: single chunks first, so that the GPU starts while most frames are
+        # still on the bus (a launch of <= 296 pairs runs one CTA per pair to completion, and launches of different
+        # groups share the SMs), but everything within two chunks of the end goes into ONE launch: with more pairs
+        # than CTAs the kernel's work queue and tail kernel balance the finish over all SMs, where short launches would
+        # each end on their longest pair.
+        chunks = [(lo, min(lo + chunk_frames, N)) for lo in range(0, N, chunk_frames)]
+        groups, k = [], 0
+        while k < len(chunks):
+            if N - chunks[k][0] <= 2 * chunk_frames:
+                groups.append(chunks[k:])
+                break
+            groups.append(chunks[k:k + 1])
+            k += 1
+        built = None  # event: the previous group's pyramids are complete
+        for gi, group in enumerate(groups):
+            s = self._streams[gi % 3]
             sp = C.c_void_p(s.cuda_stream)
-            if host:   # uploads back to back on the copy stream, compute streams wait for their chunk's event
-                self._h.call("dvo_upload_frames", lo, C.c_void_p(bgr[lo].data_ptr()), C.c_void_p(depth[lo].data_ptr()),
-                             hi - lo, cp)
-                up = torch.cuda.Event()
-                up.record(cs)
-                s.wait_event(up)
-                self._h.call("dvo_build_pyramids_staged", lo, hi - lo, 1, sp)
-            else:
-                self._h.call("dvo_build_pyramids", lo, C.c_void_p(bgr[lo].data_ptr()), C.c_void_p(depth[lo].data_ptr()),
-                             hi - lo, 1, sp)
+            for lo, hi in group:
+                if host:   # uploads back to back on the copy stream, the compute stream waits for its chunk's event
+                    self._h.call("dvo_upload_frames", lo, C.c_void_p(bgr[lo].data_ptr()),
+                                 C.c_void_p(depth[lo].data_ptr()), hi - lo, cp)
+                    up = torch.cuda.Event()
+                    up.record(cs)
+                    s.wait_event(up)
+                    self._h.call("dvo_build_pyramids_staged", lo, hi - lo, 1, sp)
+                else:
+                    self._h.call("dvo_build_pyramids", lo, C.c_void_p(bgr[lo].data_ptr()),
+                                 C.c_void_p(depth[lo].data_ptr()), hi - lo, 1, sp)
             ev = torch.cuda.Event()
             ev.record(s)
-            p0, p1 = max(lo - 1, 0), hi - 1   # pairs whose current frame is in this chunk
+            glo, ghi = group[0][0], group[-1][1]
+            p0, p1 = max(glo - 1, 0), ghi - 1   # pairs whose current frame is in this group
             if p1 > p0:
-                if built is not None and p0 < lo:
-                    s.wait_event(built)       # pair lo-1 reads frame lo-1, built on another stream
+                if built is not None and p0 < glo:
+                    s.wait_event(built)       # pair glo-1 reads frame glo-1, built on another stream
                 self._h.call("dvo_estimate", p0, p0 + 1, p1 - p0, None, None, C.c_void_p(self._qt[p0].data_ptr()),
                              C.c_void_p(self._stats[p0].data_ptr()), sp)
                 with torch.cuda.stream(s):
