@@ -1,6 +1,6 @@
 """The persistent kernel hands pairs from CTA to CTA (time slices) and leaves the last ones to a cluster kernel; neither
 may change a single bit of a result: a batch larger than the grid must equal the same pairs run in small launches
-(one CTA per pair from start to end)."""
+and in launches of one pair (one CTA per pair from start to end)."""
 import numpy as np
 import pytest
 
@@ -34,6 +34,14 @@ def test_large_batch_equals_small_launches_bitwise(dvo_mod, weights, depth):
         qt, st = small.estimate()
         assert np.array_equal(qt, qt_big[lo:lo + 100]), f"pairs {lo}.. differ between the large batch and small launches"
         assert np.array_equal(st["iters"], st_big["iters"][lo:lo + 100])
+    # launches of ONE pair never yield: one CTA runs the pair from start to end (the small launches above hand their
+    # last pairs to the tail kernel's clusters like the large one)
+    one = m.PairBatchAligner(cam, h, w, levels, max_pairs=1, weights=weights, use_depth_residual=depth)
+    for i in (0, 1, 350, 699):
+        one.build(*(x[i:i + 1].copy() for x in frames))
+        qt, st = one.estimate()
+        assert np.array_equal(qt[0], qt_big[i]), f"pair {i} differs between the batch and a one-pair launch"
+        assert np.array_equal(st["iters"][0], st_big["iters"][i])
     # and from run to run
     qt2, _ = big.estimate()
     assert np.array_equal(qt2, qt_big)
