@@ -220,12 +220,14 @@ static int create_impl(dvo_handle* h) {
             return DVO_ERR_INVALID;
         }
         const size_t n = h->lplane[l] * h->max_frames;
-        // Reads past the end of the last frame slot (align_kernel.cuh, fused_pass / depth_pass), in rows of this level:
+        // Reads past the end of the last frame slot (align_kernel.cuh, fused_pass), in rows of this level:
         //   tap records / current depth: tap coordinates are validated (inside the plane, or (0,0)), the unclamped
         //     (x0 + 1, y0 + 1) tap reads at most pitch + 1 elements past the plane, and the L1 touches run up to
         //     kMaxPrefetchRows + 1 rows ahead of a tap: kMaxPrefetchRows + 2 rows + 1 element.
-        //   previous-frame records: the software pipeline loads 2 rows past a chunk's last row and touches up to
-        //     kMaxPrefetchRows rows (+ 128 elements of lane spread) ahead of that: kMaxPrefetchRows + 3 rows.
+        //   point lists (2 words per pixel of the plane; a list never has more tiles than the plane has 128-pixel
+        //     groups): the software pipeline loads 2 tiles past a chunk's last tile and touches up to kMaxPrefetchRows
+        //     tiles (+ a tile of lane spread) ahead of that: (kMaxPrefetchRows + 3) * 256 words, which the
+        //     2 * (kMaxPrefetchRows + 4) * pitch words of slack cover because pitch >= 128.
         // One row more than needed is allocated for each.
         const size_t n_rec = n + (size_t)(kMaxPrefetchRows + 3) * (size_t)h->lpitch[l];
         const size_t n_raw = n + (size_t)(kMaxPrefetchRows + 4) * (size_t)h->lpitch[l];
