@@ -416,7 +416,7 @@ def config_single_pair(dvo, torch, dev, weights):
     return {"single_pair_step_ms": float(np.median(lat[2:])), "single_pair_kernel_ms": float(np.median(kms[2:])),
             "abs_twist_error_vs_truth": err,
             "note": "one 640x480 pair through get_dvo(...).step(color, depth): H2D of the frame, pyramids, estimate on one "
-                    "thread-block cluster of 8 CTAs, D2H of the pose"}
+                    "thread-block cluster (16 CTAs on a B200), D2H of the pose"}
 
 
 def config_sequence(torch, dvo, dev, frames, weights, reps=3):

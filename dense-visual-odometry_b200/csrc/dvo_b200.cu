@@ -263,9 +263,28 @@ static int create_impl(dvo_handle* h) {
         h->err = "threads_per_block must be 0, 128 or 256";
         return DVO_ERR_INVALID;
     }
+    if (h->cfg.cluster_size == -1) {   // the largest cluster this device can co-schedule for the latency kernel
+        h->cfg.cluster_size = 8;
+        align_fn cfn16 = get_cluster(h);
+        if (cfn16 && cudaFuncSetAttribute((const void*)cfn16, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+            cudaLaunchConfig_t lc = {};
+            lc.gridDim = dim3(16);
+            lc.blockDim = dim3(kClusterThreads);
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 16;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            lc.attrs = at;
+            lc.numAttrs = 1;
+            int n16 = 0;
+            if (cudaOccupancyMaxActiveClusters(&n16, (const void*)cfn16, &lc) == cudaSuccess && n16 >= 1) h->cfg.cluster_size = 16;
+        }
+        (void)cudaGetLastError();   // a failed query is not an error of the handle
+    }
     if (h->cfg.cluster_size != 0 && h->cfg.cluster_size != 1 && h->cfg.cluster_size != 2 && h->cfg.cluster_size != 4 &&
         h->cfg.cluster_size != 8 && h->cfg.cluster_size != 16) {
-        h->err = "cluster_size must be 0, 1, 2, 4, 8 or 16";
+        h->err = "cluster_size must be -1, 0, 1, 2, 4, 8 or 16";
         return DVO_ERR_INVALID;
     }
     {   // points_kernel keeps one count per (strip, row) of a level in shared memory

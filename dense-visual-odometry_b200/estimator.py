@@ -153,7 +153,7 @@ class RobustDVOB200:
     gpu_robust_dense_visual_odometry.py:17; if omitted the device state is created on the first frame).
     Extras, all defaulting to reference behaviour: `weights` ("none" | "tdist" | "huber"), `oob_mode`
     ("inclusive" | "strict"), `huber_k`, `max_distance`, `device`, `cluster_size` (CTAs sharing the
-    pair: 1, 2, 4, 8 or 16), `use_depth_residual` / `depth_weight` (photometric + depth residual, an extension the
+    pair: 1, 2, 4, 8 or 16; default -1 = the largest the device can co-schedule, 16 on a B200), `use_depth_residual` / `depth_weight` (photometric + depth residual, an extension the
     reference does not have; with weights "none" or "huber").
     """
 
@@ -161,7 +161,7 @@ class RobustDVOB200:
                  max_increased_steps_allowed: int = 0, sigma: float = None, tolerance: float = 1e-6,
                  max_iterations: int = 100, approximate_image2_gradient: bool = False, height: int = None,
                  width: int = None, weights: Optional[str] = None, oob_mode: str = "inclusive",
-                 huber_k: float = None, max_distance: float = 5.0, device: int = 0, cluster_size: int = 8,
+                 huber_k: float = None, max_distance: float = 5.0, device: int = 0, cluster_size: int = -1,
                  use_depth_residual: bool = False, depth_weight: float = None):
         if levels < 1 or levels > _cabi.DVO_MAX_LEVELS:
             raise ValueError(f"levels must be in [1, {_cabi.DVO_MAX_LEVELS}], got {levels}")
@@ -174,8 +174,8 @@ class RobustDVOB200:
         self._sigma = sigma
         self._max_distance = max_distance
         self._device = device
-        # one pair at a time: a thread-block cluster of `cluster_size` CTAs shares the pair (8.1 ms -> 2.0 ms per
-        # 640x480 pose at 8); the Huber/MAD weights fall back to one 256-thread CTA
+        # one pair at a time: a thread-block cluster of `cluster_size` CTAs shares the pair (kernel 6.7 ms -> 1.55 ms per
+        # 640x480 pose at 8, 1.27 ms at 16); the Huber/MAD weights fall back to one 256-thread CTA
         self._cfg = make_config(use_weighter, max_increased_steps_allowed, sigma, tolerance, max_iterations, weights,
                                 oob_mode, huber_k, max_distance, threads_per_block=256,
                                 approximate_image2_gradient=approximate_image2_gradient, cluster_size=cluster_size,

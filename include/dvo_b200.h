@@ -79,7 +79,9 @@ typedef struct dvo_config {
                                           * PREVIOUS frame's Sobel gradients at the unwarped pixel; frames used as
                                           * "previous" must then be built with_gradients != 0. default 0 */
     int32_t cluster_size;        /* 0/1 = one CTA per pair (throughput); 2, 4, 8 or 16 = one thread-block cluster per
-                                  * pair (latency of single pairs and short batches); ignored with the Huber/MAD weights */
+                                  * pair (latency of single pairs and short batches); -1 = the largest of those the
+                                  * device can co-schedule (16 needs the non-portable cluster size: 16 on a B200, else 8);
+                                  * ignored with the Huber/MAD weights */
     int32_t tdist_mean;          /* extension, with DVO_W_TDIST_REF only: 1 = the textbook t-distribution scale
                                   * (MEAN of the weighted squared residuals) instead of the reference's sum (default 0) */
     int32_t use_depth_residual;  /* extension, not in the reference: 1 = add the depth (geometric) residual
