@@ -736,6 +736,7 @@ extern "C" int dvo_estimate(dvo_handle* h, int prev_base, int cur_base, int n_pa
     }();
     align_fn tfn = (p.quantum_tiles > 0 && tail_c > 0) ? get_tail(h) : nullptr;
     p.defer = tfn ? 1 : 0;
+    if (!tfn && n_pairs <= grid) p.quantum_tiles = 0;   // no tail kernel for this variant: small launches run to completion
     align_fn fn = get_align(h);
     align_fn cfn = h->cfg.cluster_size > 1 ? get_cluster(h) : nullptr;
     const int ev = (h->ev_last + 1) & 7;
