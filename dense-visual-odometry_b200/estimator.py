@@ -543,6 +543,24 @@ class PairBatchAligner:
         return self._h.launch_count()
 
 
+def sequence_launch_groups(n_frames: int, chunk_frames: int):
+    """How SequenceAligner.align cuts a stream of host frames: a list of groups, each a list of (lo, hi) upload chunks
+    of at most chunk_frames frames; one estimate is launched per group.  Single chunks first (the GPU starts while
+    most frames are still on the bus), and everything within two chunks of the end as ONE group (a launch with more
+    pairs than CTAs is balanced over the SMs by the kernel's work queue and finished by its tail kernel)."""
+    if chunk_frames < 1:
+        raise ValueError("chunk_frames must be positive")
+    chunks = [(lo, min(lo + chunk_frames, n_frames)) for lo in range(0, n_frames, chunk_frames)]
+    groups, k = [], 0
+    while k < len(chunks):
+        if n_frames - chunks[k][0] <= 2 * chunk_frames:
+            groups.append(chunks[k:])
+            break
+        groups.append(chunks[k:k + 1])
+        k += 1
+    return groups
+
+
 class SequenceAligner:
     """A stream of N frames -> N-1 relative poses in one go (BASELINE.json configs[2]).
 
@@ -608,14 +626,7 @@ class SequenceAligner:
         # groups share the SMs), but everything within two chunks of the end goes into ONE launch: with more pairs
         # than CTAs the kernel's work queue and tail kernel balance the finish over all SMs, where short launches would
         # each end on their longest pair.
-        chunks = [(lo, min(lo + chunk_frames, N)) for lo in range(0, N, chunk_frames)]
-        groups, k = [], 0
-        while k < len(chunks):
-            if N - chunks[k][0] <= 2 * chunk_frames:
-                groups.append(chunks[k:])
-                break
-            groups.append(chunks[k:k + 1])
-            k += 1
+        groups = sequence_launch_groups(N, chunk_frames)
         built = None  # event: the previous group's pyramids are complete
         for gi, group in enumerate(groups):
             s = self._streams[gi % 3]

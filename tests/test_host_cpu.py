@@ -144,3 +144,23 @@ def test_ctypes_structs_match_the_c_header(built, tmp_path):
     assert int(out["DVO_MAX_LEVELS"]) == _cabi.DVO_MAX_LEVELS and int(out["DVO_ACC_TERMS"]) == _cabi.DVO_ACC_TERMS
     assert out["W"].split() == [str(v) for v in (_cabi.W_NONE, _cabi.W_TDIST_REF, _cabi.W_HUBER, _cabi.W_HUBER_MAD)]
     assert out["OOB"].split() == [str(_cabi.OOB_INCLUSIVE), str(_cabi.OOB_STRICT)]
+
+
+def test_sequence_launch_groups(built):
+    """SequenceAligner.align: upload chunks cover the frames once, in order; single-chunk groups first, everything
+    within two chunks of the end as one group (so the last launch has more pairs than CTAs whenever the stream allows)."""
+    from dense_visual_odometry_b200.estimator import sequence_launch_groups as groups
+    for n, c in ((1000, 256), (600, 256), (512, 256), (300, 256), (2, 256), (1000, 64), (1025, 256), (999, 1000)):
+        g = groups(n, c)
+        flat = [ch for grp in g for ch in grp]
+        assert flat[0][0] == 0 and flat[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(flat, flat[1:]))          # contiguous, no overlap
+        assert all(0 < hi - lo <= c for lo, hi in flat)
+        assert all(len(grp) == 1 for grp in g[:-1])                        # single chunks before the last group
+        assert n - g[-1][0][0] <= 2 * c                                    # the last group: within two chunks of the end
+        if len(g) > 1:
+            assert n - g[-2][0][0] > 2 * c
+    assert groups(1000, 256) == [[(0, 256)], [(256, 512)], [(512, 768), (768, 1000)]]
+    assert groups(1000, 1000) == [[(0, 1000)]]
+    with pytest.raises(ValueError):
+        groups(10, 0)
