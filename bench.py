@@ -249,7 +249,10 @@ def algorithmic_bytes(iters, px, weights="none", depth=False):
     return pxit * b, pxit
 
 
-def roofline_record(stats, px, kernel_ms, weights="none", depth=False, levels=LEVELS):
+def roofline_record(stats, px, kernel_ms, weights="none", depth=False, levels=LEVELS, depth_valid=None):
+    """depth_valid: fraction of the previous frames' level-0 pixels that have depth.  The kernel walks only those
+    (point lists); `achieved` keeps SURVEY 8d's dense count (every pixel of a level, as the reference's planes are
+    read), and `frac_touched_pixels_only` says what the fraction is when only walked pixels are counted."""
     iters = stats["iters"][:, :levels]
     ab, pxit = algorithmic_bytes(iters, px, weights, depth)
     peak, peak_src = measured_peak()
@@ -258,6 +261,9 @@ def roofline_record(stats, px, kernel_ms, weights="none", depth=False, levels=LE
            "kernel": "align_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": ab,
            "pixel_iterations_per_launch": pxit, "peak_source": peak_src,
            "gn_iterations_per_pose_mean": float(iters.sum(1).mean())}
+    if depth_valid is not None:
+        rec["depth_valid_fraction"] = float(depth_valid)
+        rec["frac_touched_pixels_only"] = float(depth_valid) * achieved / peak
     t = ncu_traffic_per_pixel_iteration()
     rec["traffic"] = None
     if t and weights == "none" and not depth:
@@ -381,7 +387,9 @@ def config_batch(torch, dvo, dev, height, width, levels, pairs, steps, weights="
     rec = {"workload": f"{pairs} synthetic {width}x{height} pairs, {levels}-level pyramid, weights={weights}"
                        + (", photometric + depth residual" if depth else ""),
            "value": pairs * steps / (ms / 1e3), "unit": UNIT, "steps": steps, "ms_per_step": ms / steps,
-           "roofline": roofline_record(stats, px, kernel_ms, weights, depth, levels), "gpu_launches": int(launches),
+           "roofline": roofline_record(stats, px, kernel_ms, weights, depth, levels,
+                                       depth_valid=float((tensors[1].view(torch.int16) != 0).float().mean().item())),
+           "gpu_launches": int(launches),
            "max_abs_twist_error_vs_truth": float(err.max()), "frac_within_1e-4": float((err < 1e-4).mean()),
            "flags_nonzero": int((stats["flags"] != 0).sum())}
     if e2e:
@@ -539,7 +547,8 @@ def gpu_arm(args):
     qt_h = qt.cpu().numpy()
     stats = dvo.stats_to_numpy(st.cpu().numpy())
     px = level_pixels()
-    roof = roofline_record(stats, px, kernel_ms, args.weights, args.depth_residual)
+    roof = roofline_record(stats, px, kernel_ms, args.weights, args.depth_residual,
+                           depth_valid=float((tensors[1][:B].view(torch.int16) != 0).float().mean().item()))
 
     # ---------------- end-to-end leg: host (pinned) buffers through the public API ----------------
     hb = [torch.empty(x.shape, dtype=x.dtype).pin_memory() for x in tensors]
